@@ -1,0 +1,61 @@
+"""ctypes binding of libapnetg.so (include/ap_netg.h). No fallback: a missing or unloadable library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libapnetg.so")
+
+AP_PREC_FP32X3 = 0
+AP_PREC_BF16 = 1
+AP_PREC_FP32_SIMT = 2
+PRECISIONS = {"fp32": AP_PREC_FP32X3, "fp32x3": AP_PREC_FP32X3, "bf16": AP_PREC_BF16, "fp32_simt": AP_PREC_FP32_SIMT}
+
+# every symbol include/ap_netg.h declares: (restype, argtypes)
+_FP = C.POINTER(C.c_float)
+SYMBOLS = {
+    "ap_netg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
+    "ap_netg_destroy": (C.c_int, [C.c_void_p]),
+    "ap_netg_load_weights": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "ap_netg_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "ap_netg_forward": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "ap_netg_forward_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "ap_netg_last_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ap_netg_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.c_void_p]),
+    "ap_conv2d_debug": (C.c_int, [C.c_int] * 12 + [C.c_void_p] * 5),
+    "ap_last_error": (C.c_char_p, []),
+    "ap_version": (C.c_char_p, []),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class ApNetgError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load libapnetg.so once. Raises ApNetgError when it has not been built (python -m animateportrait_b200.build)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ApNetgError(f"{LIB_PATH} not found: build it with `python -m animateportrait_b200.build` "
+                                  "(there is no CPU or PyTorch fallback for the generator)")
+            l = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(l, name)  # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ap_last_error()
+        raise ApNetgError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

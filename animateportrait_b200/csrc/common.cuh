@@ -1,0 +1,164 @@
+// Shared declarations of libapnetg (B200 / sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ap_netg.h"
+
+namespace ap {
+
+void set_error(const char* fmt, ...);
+
+#define AP_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ap::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return AP_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define AP_TRY(call)            \
+  do {                          \
+    int _r = (call);            \
+    if (_r != AP_OK) return _r; \
+  } while (0)
+
+#define AP_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      ap::set_error(__VA_ARGS__);   \
+      return (code);                \
+    }                               \
+  } while (0)
+
+// Activation formats in HBM. All activations are NHWC; `pad` is a halo of that many pixels on each
+// side of H and W that the PRODUCER fills (reflection) or leaves zero.
+enum ActFmt : int {
+  FMT_F32 = 0,     // one fp32 plane
+  FMT_BF16X2 = 1,  // two bf16 planes: hi = bf16(x), lo = bf16(x - hi)   (fp32-accurate tcgen05 operands)
+  FMT_BF16 = 2     // one bf16 plane
+};
+
+struct Act {
+  int B = 0, H = 0, W = 0, C = 0;  // C = channels of the whole buffer (concats are channel offsets)
+  int pad = 0;
+  int fmt = FMT_F32;
+  void* p0 = nullptr;  // fp32 plane or bf16 hi plane
+  void* p1 = nullptr;  // bf16 lo plane (FMT_BF16X2)
+  size_t pixels() const { return (size_t)B * (H + 2 * pad) * (W + 2 * pad); }
+  size_t elems() const { return pixels() * C; }
+};
+
+// Raw (pre-InstanceNorm) conv output: fp32 NHWC, no halo, plus per-(n,c) {sum, sumsq} in double.
+struct Raw {
+  int B = 0, H = 0, W = 0, C = 0;
+  float* p = nullptr;
+  double* stats = nullptr;  // [B][C][2], zeroed at the start of every forward
+};
+
+constexpr int AP_MAX_TAPS = 49;
+struct ConvTaps {
+  int n;
+  int8_t dy[AP_MAX_TAPS];  // input offset of tap t relative to  y_virtual*stride
+  int8_t dx[AP_MAX_TAPS];
+  uint8_t slab[AP_MAX_TAPS];  // which [ky*kw+kx] weight slab the tap multiplies
+};
+
+// One convolution "problem": a set of taps applied on a virtual output grid Hv x Wv (the input grid
+// for the phases of a transposed conv), scattered to out[(y*os+py, x*os+px)].
+struct ConvGeom {
+  int B;
+  int Hin, Win, Cin;   // logical input (without halo)
+  int Hv, Wv;          // virtual output grid
+  int stride;          // input step per virtual output pixel
+  int reflect;         // 1: reflection padding, 0: zero padding
+  int Cout;
+  int os, py, px;      // output scatter
+  int Hout, Wout;
+  ConvTaps taps;
+};
+
+struct SimtConvP {
+  ConvGeom g;
+  const float* in;  // fp32, NHWC (in_C channels per pixel, first channel in_coff) or NCHW
+  int in_nchw;
+  int in_C, in_coff;
+  const float* wpk;  // [slab][Cin][Cout] fp32
+  float* out;        // raw NHWC
+  int out_C, out_coff;
+  double* stats;  // may be null; indexed [(n*stat_C + stat_coff + c)*2]
+  int stat_C, stat_coff;
+};
+
+struct ApplyP {
+  const float* raw; int raw_C, raw_coff;
+  const double* stats; int stat_C, stat_coff;  // null -> no normalisation (bias mode)
+  const float* bias;                           // null or [C]
+  const float* raw2; int raw2_C, raw2_coff;    // optional second InstanceNorm'ed operand (ResnetBlock2 shortcut)
+  const double* stats2; int stat2_C, stat2_coff;
+  const float* res_in;  // optional fp32 residual stream [B,H,W,C] added to the result
+  float* res_out;       // optional: result written here as fp32 [B,H,W,C]
+  int relu;
+  int B, H, W, C;
+  // destination (may be absent: fmt = -1)
+  int fmt; void* d0; void* d1; int dC, dcoff, dpad;
+  int halo_reflect;  // fill the halo ring by reflection (pad==1)
+};
+
+struct WarpP {
+  const float* raw; int raw_C, raw_coff;       // raw stem/conv output, normalised + ReLU on the fly
+  const double* stats; int stat_C, stat_coff;
+  const float* motion;  // [B,256,256,2]
+  const float* flow;    // [B,2,256,256]
+  const float* ifmask;  // [B,1,256,256]
+  int B, S, C, level;   // feature size S, feature channels C, pyramid level 0/1/2
+  int fmt; void* d0; void* d1; int dC, dcoff, dpad;  // output: 2C channels at dcoff
+};
+
+struct OutConvP {
+  const float* raw; const double* stats;  // model3.3 raw output [B,256,256,64] + stats (IN+ReLU on the fly)
+  const float* w;                         // [onc][49][64] fp32
+  const float* bias;                      // [onc]
+  float* out;                             // NCHW [B,onc,256,256]
+  int B, onc;
+};
+
+struct ReadP {  // debug tap: Act or Raw(+stats) -> NCHW fp32
+  int B, H, W, C;      // logical view
+  int fmt; const void* p0; const void* p1; int sC, scoff, spad;
+  const double* stats; int stat_C, stat_coff; int relu;  // stats != null: normalise
+  float* dst;
+};
+
+// ---- launchers (each returns AP_OK / error and counts one launch) ----
+int launch_conv_simt(const SimtConvP& p, cudaStream_t st);
+int launch_apply(const ApplyP& p, cudaStream_t st);
+int launch_warp(const WarpP& p, cudaStream_t st);
+int launch_out_conv(const OutConvP& p, cudaStream_t st);
+int launch_read(const ReadP& p, cudaStream_t st);
+// weight packing: src torch layout -> [slab][Cin][simt_C] fp32 at column simt_coff (simt) and/or
+// [slab][Cout][Cin] bf16 hi,lo (umma)
+int launch_pack_weights(const float* src, int Cout, int Cin, int k, int transposed, float* dst_simt, int simt_C,
+                        int simt_coff, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, cudaStream_t st);
+int64_t launches_get();
+void launches_add(int n);
+int launch_pack_out_weights(const float* src, int onc, float* dst, cudaStream_t st);
+int launch_nchw_to_act(const float* src, const Act& dst, cudaStream_t st);  // debug conv helper
+
+// ---- tcgen05 conv ----
+struct UmmaConv;  // opaque launch record (tensor maps + params), see conv_umma.cu
+int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff,
+                     const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int nprod,
+                     float* out_raw, int out_C, int out_coff, double* stats, int stat_C, int stat_coff);
+void umma_conv_destroy(UmmaConv* c);
+int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
+int umma_init();  // resolves cuTensorMapEncodeTiled, sets func attributes
+
+ConvTaps make_taps_conv(int k, int pad, int extra_origin);
+ConvTaps make_taps_convT_phase(int py, int px);
+
+}  // namespace ap

@@ -1,0 +1,382 @@
+// HBM-bound kernels of the generator: InstanceNorm apply (+ReLU, +residual, +halo, +bf16 hi/lo split),
+// the fused double feature warp, weight packing and the debug tap reader.
+#include "common.cuh"
+
+namespace ap {
+
+void launches_add(int n);
+
+// ------------------------------------------------------------------------------------------------
+// destination writer shared by apply / warp: 4 consecutive channels of one pixel, any ActFmt,
+// optional reflected halo (pad == 1).
+// ------------------------------------------------------------------------------------------------
+struct Dst {
+  int fmt; void* d0; void* d1; int C, coff, pad, H, W, halo_reflect;
+};
+
+__device__ __forceinline__ void store4(const Dst& d, size_t pix_index, int c, float4 v) {
+  const size_t off = pix_index * d.C + d.coff + c;
+  if (d.fmt == FMT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.d0) + off) = v;
+  } else {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y),
+                        h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    __nv_bfloat162 a, b;
+    a.x = h0; a.y = h1; b.x = h2; b.y = h3;
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.d0) + off) = pk;
+    if (d.fmt == FMT_BF16X2) {
+      a.x = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+      a.y = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+      b.x = __float2bfloat16_rn(v.z - __bfloat162float(h2));
+      b.y = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.d1) + off) = pk;
+    }
+  }
+}
+
+// writes pixel (n,y,x) and, with halo_reflect, its mirror images in the halo ring
+__device__ __forceinline__ void store_pixel(const Dst& d, int n, int y, int x, int c, float4 v) {
+  const int Hp = d.H + 2 * d.pad, Wp = d.W + 2 * d.pad;
+  const size_t base = (size_t)n * Hp;
+  store4(d, (base + y + d.pad) * Wp + x + d.pad, c, v);
+  if (d.halo_reflect && d.pad == 1) {
+    const int ry = (y == 1) ? 0 : ((y == d.H - 2) ? d.H + 1 : -1);
+    const int rx = (x == 1) ? 0 : ((x == d.W - 2) ? d.W + 1 : -1);
+    if (ry >= 0) store4(d, (base + ry) * Wp + x + 1, c, v);
+    if (rx >= 0) store4(d, (base + y + 1) * Wp + rx, c, v);
+    if (ry >= 0 && rx >= 0) store4(d, (base + ry) * Wp + rx, c, v);
+  }
+}
+
+__device__ __forceinline__ void stats_to_affine(const double* st, int n, int stat_C, int stat_coff, int c,
+                                                double inv_n, float* mean, float* rstd) {
+  const double su = st[((size_t)n * stat_C + stat_coff + c) * 2 + 0];
+  const double sq = st[((size_t)n * stat_C + stat_coff + c) * 2 + 1];
+  const double m = su * inv_n;
+  double var = sq * inv_n - m * m;
+  if (var < 0.0) var = 0.0;
+  *mean = (float)m;
+  *rstd = (float)(1.0 / sqrt(var + 1e-5));  // eps of nn.InstanceNorm2d (networks.py:34)
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply: y = IN(raw) [+ IN(raw2)] [+ bias] [+ res_in], optional ReLU; -> res_out (fp32) and/or dst.
+// grid (pixel chunks, B); each thread handles 4 channels of one pixel per iteration.
+// ------------------------------------------------------------------------------------------------
+constexpr int APPLY_PIX_PER_CTA = 128;
+
+__global__ void __launch_bounds__(256) apply_kernel(const ApplyP p) {
+  __shared__ float s_mean[256], s_rstd[256], s_mean2[256], s_rstd2[256];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const double inv_n = 1.0 / (double)(p.H * p.W);
+  for (int c = tid; c < p.C; c += 256) {
+    if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c, inv_n, &s_mean[c], &s_rstd[c]);
+    else { s_mean[c] = p.bias ? -p.bias[c] : 0.f; s_rstd[c] = 1.f; }
+    if (p.raw2) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c, inv_n, &s_mean2[c], &s_rstd2[c]);
+  }
+  __syncthreads();
+  Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
+  const int tpp = p.C >> 2;  // threads per pixel
+  const int HW = p.H * p.W;
+  const int pix0 = blockIdx.x * APPLY_PIX_PER_CTA;
+  const int pix1 = min(pix0 + APPLY_PIX_PER_CTA, HW);
+  for (int i = tid; i < (pix1 - pix0) * tpp; i += 256) {
+    const int pix = pix0 + i / tpp;
+    const int c = (i % tpp) * 4;
+    const size_t gp = (size_t)n * HW + pix;
+    float4 v = *reinterpret_cast<const float4*>(p.raw + gp * p.raw_C + p.raw_coff + c);
+    v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
+    v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
+    v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
+    v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
+    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (p.raw2) {
+      const float4 u = *reinterpret_cast<const float4*>(p.raw2 + gp * p.raw2_C + p.raw2_coff + c);
+      v.x += (u.x - s_mean2[c + 0]) * s_rstd2[c + 0];
+      v.y += (u.y - s_mean2[c + 1]) * s_rstd2[c + 1];
+      v.z += (u.z - s_mean2[c + 2]) * s_rstd2[c + 2];
+      v.w += (u.w - s_mean2[c + 3]) * s_rstd2[c + 3];
+    }
+    if (p.res_in) {
+      const float4 r = *reinterpret_cast<const float4*>(p.res_in + gp * p.C + c);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (p.res_out) *reinterpret_cast<float4*>(p.res_out + gp * p.C + c) = v;
+    if (p.fmt >= 0) {
+      const int y = pix / p.W, x = pix - y * p.W;
+      store_pixel(d, n, y, x, c, v);
+    }
+  }
+}
+
+int launch_apply(const ApplyP& p, cudaStream_t st) {
+  AP_REQUIRE(p.C % 4 == 0 && p.C <= 256, AP_ERR_INVALID, "apply: C=%d must be a multiple of 4 and <= 256", p.C);
+  AP_REQUIRE(p.raw_C % 4 == 0 && p.raw_coff % 4 == 0, AP_ERR_INVALID, "apply: raw channel layout not 16B aligned");
+  AP_REQUIRE(p.fmt < 0 || (p.dC % 4 == 0 && p.dcoff % 4 == 0), AP_ERR_INVALID, "apply: dst channel layout");
+  dim3 grid((p.H * p.W + APPLY_PIX_PER_CTA - 1) / APPLY_PIX_PER_CTA, p.B);
+  apply_kernel<<<grid, 256, 0, st>>>(p);
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  return AP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// double feature warp (networks.py:1298-1313 + intrinsic_flow_models/modules.py:596-625).
+// Arithmetic follows oracle/netg_oracle.py::double_feature_warping_closed_form in
+// PyTorch's op order; __f*_rn intrinsics keep nvcc from contracting the coordinate math into FMAs.
+// ------------------------------------------------------------------------------------------------
+struct Lerp { int i0, i1; float l0, l1; };
+
+__device__ __forceinline__ Lerp src_index_ac_true(int dst, float scale, int in_size) {
+  // upsample_bilinear2d(align_corners=True): src = scale*dst; i0 = (int)src; l1 = src - i0
+  const float real = __fmul_rn(scale, (float)dst);
+  Lerp r;
+  r.i0 = (int)real;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = fminf(fmaxf(__fsub_rn(real, (float)r.i0), 0.f), 1.f);
+  r.l0 = __fsub_rn(1.f, r.l1);
+  return r;
+}
+
+__device__ __forceinline__ float bilerp(const float* __restrict__ plane, int stride_x, int W, const Lerp& ly,
+                                        const Lerp& lx) {
+  const float v00 = plane[((size_t)ly.i0 * W + lx.i0) * stride_x];
+  const float v01 = plane[((size_t)ly.i0 * W + lx.i1) * stride_x];
+  const float v10 = plane[((size_t)ly.i1 * W + lx.i0) * stride_x];
+  const float v11 = plane[((size_t)ly.i1 * W + lx.i1) * stride_x];
+  const float top = __fadd_rn(__fmul_rn(lx.l0, v00), __fmul_rn(lx.l1, v01));
+  const float bot = __fadd_rn(__fmul_rn(lx.l0, v10), __fmul_rn(lx.l1, v11));
+  return __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+}
+
+__device__ __forceinline__ float unnormalize_ac_false(float g, int S) {
+  // grid_sampler_unnormalize(align_corners=False): ((g + 1) * S - 1) / 2
+  return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)S), 1.f), 2.f);
+}
+
+struct Taps4 { int off[4]; float w[4]; };  // pixel offsets (y*S+x) or -1, weights in order nw, ne, sw, se
+
+__device__ __forceinline__ Taps4 make_taps4(float ix, float iy, int S) {
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  // ATen's CPU grid sampler (the oracle): w = x - floor(x), e = 1 - w; nw = s*e, ne = s*w, sw = n*e, se = n*w
+  const float wx = __fsub_rn(ix, fx), wy = __fsub_rn(iy, fy);
+  const float ex = __fsub_rn(1.f, wx), ey = __fsub_rn(1.f, wy);
+  Taps4 t;
+  t.w[0] = __fmul_rn(ex, ey); t.w[1] = __fmul_rn(wx, ey); t.w[2] = __fmul_rn(ex, wy); t.w[3] = __fmul_rn(wx, wy);
+  const bool x0ok = (x0 >= 0) && (x0 < S), x1ok = (x0 + 1 >= 0) && (x0 + 1 < S);
+  const bool y0ok = (y0 >= 0) && (y0 < S), y1ok = (y0 + 1 >= 0) && (y0 + 1 < S);
+  t.off[0] = (x0ok && y0ok) ? y0 * S + x0 : -1;
+  t.off[1] = (x1ok && y0ok) ? y0 * S + x0 + 1 : -1;
+  t.off[2] = (x0ok && y1ok) ? (y0 + 1) * S + x0 : -1;
+  t.off[3] = (x1ok && y1ok) ? (y0 + 1) * S + x0 + 1 : -1;
+  return t;
+}
+
+__global__ void __launch_bounds__(256) warp_kernel(const WarpP p) {
+  __shared__ float s_mean[128], s_rstd[128];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int S = p.S, C = p.C;
+  const double inv_n = 1.0 / (double)(S * S);
+  for (int c = tid; c < C; c += 256) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c, inv_n, &s_mean[c], &s_rstd[c]);
+  __syncthreads();
+
+  const int tpp = C >> 2;
+  const int ppc = 256 / tpp;  // pixels per CTA iteration
+  const int pix = blockIdx.x * ppc + tid / tpp;
+  if (pix >= S * S) return;
+  const int c = (tid % tpp) * 4;
+  const int i = pix / S, j = pix - i * S;
+
+  // conditioning at this pixel (level > 0: bilinear resize of the 256x256 maps, align_corners=True)
+  float mx, my, fx, fy, mk;
+  const float* mo = p.motion + (size_t)n * 256 * 256 * 2;
+  const float* fl = p.flow + (size_t)n * 2 * 256 * 256;
+  const float* ms = p.ifmask + (size_t)n * 256 * 256;
+  if (p.level == 0) {
+    mx = mo[(size_t)pix * 2 + 0]; my = mo[(size_t)pix * 2 + 1];
+    fx = fl[pix]; fy = fl[256 * 256 + pix];
+    mk = ms[pix];
+  } else {
+    const float scale = 255.f / (float)(S - 1);  // fp32((in-1)/(out-1))
+    const Lerp ly = src_index_ac_true(i, scale, 256), lx = src_index_ac_true(j, scale, 256);
+    mx = bilerp(mo + 0, 2, 256, ly, lx);
+    my = bilerp(mo + 1, 2, 256, ly, lx);
+    const float fs = (p.level == 1) ? 0.5f : 0.25f;  // flow / 2**level before the resize (exact)
+    // scaling by a power of two commutes exactly with the interpolation arithmetic
+    fx = bilerp(fl, 1, 256, ly, lx) * fs;
+    fy = bilerp(fl + 256 * 256, 1, 256, ly, lx) * fs;
+    mk = bilerp(ms, 1, 256, ly, lx);
+  }
+  // motion warp: F.grid_sample(x, motion) with default align_corners=False
+  const Taps4 tm = make_taps4(unnormalize_ac_false(mx, S), unnormalize_ac_false(my, S), S);
+  // flow warp: grid = 2*(j + f)/(S-1) - 1, then the same un-normalisation
+  const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)j, fx)), (float)(S - 1)), 1.f);
+  const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)i, fy)), (float)(S - 1)), 1.f);
+  const Taps4 tf = make_taps4(unnormalize_ac_false(gx, S), unnormalize_ac_false(gy, S), S);
+
+  const float4 mean = *reinterpret_cast<const float4*>(&s_mean[c]);
+  const float4 rstd = *reinterpret_cast<const float4*>(&s_rstd[c]);
+  const float* src = p.raw + (size_t)n * S * S * p.raw_C + p.raw_coff + c;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (tm.off[t] >= 0) {
+      float4 v = *reinterpret_cast<const float4*>(src + (size_t)tm.off[t] * p.raw_C);
+      v.x = fmaxf((v.x - mean.x) * rstd.x, 0.f); v.y = fmaxf((v.y - mean.y) * rstd.y, 0.f);
+      v.z = fmaxf((v.z - mean.z) * rstd.z, 0.f); v.w = fmaxf((v.w - mean.w) * rstd.w, 0.f);
+      a.x = fmaf(v.x, tm.w[t], a.x); a.y = fmaf(v.y, tm.w[t], a.y);
+      a.z = fmaf(v.z, tm.w[t], a.z); a.w = fmaf(v.w, tm.w[t], a.w);
+    }
+    if (tf.off[t] >= 0) {
+      float4 v = *reinterpret_cast<const float4*>(src + (size_t)tf.off[t] * p.raw_C);
+      v.x = fmaxf((v.x - mean.x) * rstd.x, 0.f); v.y = fmaxf((v.y - mean.y) * rstd.y, 0.f);
+      v.z = fmaxf((v.z - mean.z) * rstd.z, 0.f); v.w = fmaxf((v.w - mean.w) * rstd.w, 0.f);
+      b.x = fmaf(v.x, tf.w[t], b.x); b.y = fmaf(v.y, tf.w[t], b.y);
+      b.z = fmaf(v.z, tf.w[t], b.z); b.w = fmaf(v.w, tf.w[t], b.w);
+    }
+  }
+  if (!(mk > 0.5f)) b = make_float4(-1.f, -1.f, -1.f, -1.f);  // torch.where(mask > 0.5, out, -1)
+  Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, S, S, 0};
+  store_pixel(d, n, i, j, c, a);
+  store_pixel(d, n, i, j, C + c, b);
+}
+
+int launch_warp(const WarpP& p, cudaStream_t st) {
+  AP_REQUIRE(p.C == 32 || p.C == 64 || p.C == 128, AP_ERR_INVALID, "warp: C=%d", p.C);
+  const int tpp = p.C / 4, ppc = 256 / tpp;
+  dim3 grid((p.S * p.S + ppc - 1) / ppc, p.B);
+  warp_kernel<<<grid, 256, 0, st>>>(p);
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  return AP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (runs once per load_state_dict)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ src, int Cout, int Cin, int k, int transposed,
+                                    float* dst_simt, int simt_C, int simt_coff, __nv_bfloat16* dst_hi,
+                                    __nv_bfloat16* dst_lo) {
+  const size_t total = (size_t)Cout * Cin * k * k;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    // i enumerates (slab, co, ci)
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int slab = (int)(i / ((size_t)Cin * Cout));
+    const size_t s = transposed ? (((size_t)ci * Cout + co) * k * k + slab)   // ConvTranspose2d [Cin,Cout,kh,kw]
+                                : (((size_t)co * Cin + ci) * k * k + slab);   // Conv2d [Cout,Cin,kh,kw]
+    const float w = src[s];
+    if (dst_simt) dst_simt[((size_t)slab * Cin + ci) * simt_C + simt_coff + co] = w;
+    if (dst_hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      dst_hi[i] = h;  // [slab][Cout][Cin]
+      if (dst_lo) dst_lo[i] = __float2bfloat16_rn(w - __bfloat162float(h));
+    }
+  }
+}
+
+int launch_pack_weights(const float* src, int Cout, int Cin, int k, int transposed, float* dst_simt, int simt_C,
+                        int simt_coff, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, cudaStream_t st) {
+  const size_t total = (size_t)Cout * Cin * k * k;
+  const int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(src, Cout, Cin, k, transposed, dst_simt, simt_C, simt_coff, dst_hi,
+                                              dst_lo);
+  AP_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+__global__ void pack_out_weights_kernel(const float* __restrict__ src, int onc, float* dst) {
+  // src [onc][64][7][7] -> dst [onc][49][64]
+  const int total = onc * 49 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % 64, t = (i / 64) % 49, o = i / (64 * 49);
+    dst[i] = src[((size_t)o * 64 + c) * 49 + t];
+  }
+}
+
+int launch_pack_out_weights(const float* src, int onc, float* dst, cudaStream_t st) {
+  pack_out_weights_kernel<<<(onc * 49 * 64 + 255) / 256, 256, 0, st>>>(src, onc, dst);
+  AP_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug: activation -> NCHW fp32;  NCHW fp32 -> activation (for ap_conv2d_debug)
+// ------------------------------------------------------------------------------------------------
+__global__ void read_kernel(const ReadP p) {
+  const size_t total = (size_t)p.B * p.C * p.H * p.W;
+  const double inv_n = 1.0 / (double)(p.H * p.W);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.W);
+    const int y = (int)((i / p.W) % p.H);
+    const int c = (int)((i / ((size_t)p.W * p.H)) % p.C);
+    const int n = (int)(i / ((size_t)p.W * p.H * p.C));
+    const size_t pix = ((size_t)n * (p.H + 2 * p.spad) + y + p.spad) * (p.W + 2 * p.spad) + x + p.spad;
+    const size_t off = pix * p.sC + p.scoff + c;
+    float v;
+    if (p.fmt == FMT_F32) v = reinterpret_cast<const float*>(p.p0)[off];
+    else {
+      v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.p0)[off]);
+      if (p.fmt == FMT_BF16X2) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.p1)[off]);
+    }
+    if (p.stats) {
+      float m, r;
+      stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c, inv_n, &m, &r);
+      v = (v - m) * r;
+      if (p.relu) v = fmaxf(v, 0.f);
+    }
+    p.dst[i] = v;
+  }
+}
+
+int launch_read(const ReadP& p, cudaStream_t st) {
+  read_kernel<<<1184, 256, 0, st>>>(p);
+  AP_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+__global__ void nchw_to_act_kernel(const float* __restrict__ src, Act d) {
+  const size_t total = (size_t)d.B * d.C * d.H * d.W;
+  const int Hp = d.H + 2 * d.pad, Wp = d.W + 2 * d.pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d.C);
+    const int x = (int)((i / d.C) % d.W);
+    const int y = (int)((i / ((size_t)d.C * d.W)) % d.H);
+    const int n = (int)(i / ((size_t)d.C * d.W * d.H));
+    const float v = src[(((size_t)n * d.C + c) * d.H + y) * d.W + x];
+    // interior + reflected halo (pad 1), same rule as store_pixel
+    int ys[2] = {y + d.pad, -1}, xs[2] = {x + d.pad, -1};
+    if (d.pad == 1) {
+      ys[1] = (y == 1) ? 0 : ((y == d.H - 2) ? d.H + 1 : -1);
+      xs[1] = (x == 1) ? 0 : ((x == d.W - 2) ? d.W + 1 : -1);
+    }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        if (ys[a] < 0 || xs[b] < 0) continue;
+        const size_t off = (((size_t)n * Hp + ys[a]) * Wp + xs[b]) * d.C + c;
+        if (d.fmt == FMT_F32) reinterpret_cast<float*>(d.p0)[off] = v;
+        else {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          reinterpret_cast<__nv_bfloat16*>(d.p0)[off] = h;
+          if (d.fmt == FMT_BF16X2)
+            reinterpret_cast<__nv_bfloat16*>(d.p1)[off] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+      }
+  }
+}
+
+int launch_nchw_to_act(const float* src, const Act& dst, cudaStream_t st) {
+  nchw_to_act_kernel<<<1184, 256, 0, st>>>(src, dst);
+  AP_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+}  // namespace ap

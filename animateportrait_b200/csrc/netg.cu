@@ -1,0 +1,689 @@
+// Handle, weight loading, workspace planning, the forward schedule and the C ABI (include/ap_netg.h)
+// of the B200-native generator `ResnetConditionTriGenerator32_full_ifw`
+// (reference: Module2/models/networks.py:1190-1340).
+//
+// The forward schedule is written once (Runner::run) and interpreted in three phases:
+//   SIZE  - walk the graph, add up workspace bytes
+//   BUILD - same walk with real pointers: creates the TMA tensor maps of every tcgen05 conv, records debug taps
+//   EXEC  - same walk, launching kernels on the caller's stream
+// so buffer assignment, tensor maps and launches can never disagree.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ap {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap_;
+  va_start(ap_, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap_);
+  va_end(ap_);
+}
+
+struct LayerSpec {
+  std::string name;
+  int cout, cin, k;
+  bool transposed;
+};
+
+static std::vector<LayerSpec> layer_specs(int onc) {
+  std::vector<LayerSpec> v;
+  v.push_back({"model_tri_merge", 256, 768, 3, false});
+  v.push_back({"model_tri00.1", 32, 3, 7, false});
+  v.push_back({"model_tri01.0", 128, 64, 3, false});
+  v.push_back({"model_tri02.0", 256, 128, 3, false});
+  v.push_back({"model_tri10.1", 64, 3, 7, false});
+  v.push_back({"model_tri11.0", 64, 64, 3, false});
+  v.push_back({"model_tri12.0", 256, 128, 3, false});
+  v.push_back({"model_tri20.1", 64, 3, 7, false});
+  v.push_back({"model_tri21.0", 128, 64, 3, false});
+  v.push_back({"model_tri22.0", 128, 128, 3, false});
+  for (int i = 0; i < 9; ++i) {
+    const std::string b = "model2." + std::to_string(i);
+    const bool b2 = (i + 3) % 3 == 0;  // (i + disp) % div == 0, networks.py:1259
+    v.push_back({b + ".conv_block.1", 256, b2 ? 288 : 256, 3, false});
+    v.push_back({b + ".conv_block.5", 256, 256, 3, false});
+    if (b2) v.push_back({b + ".shortcut.0", 256, 288, 3, false});
+  }
+  v.push_back({"model3.0", 128, 256, 3, true});
+  v.push_back({"model3.3", 64, 128, 3, true});
+  v.push_back({"model3.7", onc, 64, 7, false});
+  v.push_back({"model_landmark_trans.0", 8, 1, 3, false});
+  v.push_back({"model_landmark_trans.3", 16, 8, 3, false});
+  v.push_back({"model_landmark_trans.6", 16, 16, 3, false});
+  return v;
+}
+
+struct LayerW {
+  int cout = 0, cin = 0, k = 0;
+  float* simt = nullptr;          // [slab][Cin][Cout]
+  __nv_bfloat16* hi = nullptr;    // [slab][Cout][Cin]
+  __nv_bfloat16* lo = nullptr;
+};
+
+struct TapRec {
+  int B, H, W, C;
+  int fmt; const void* p0; const void* p1; int sC, scoff, spad;
+  const double* stats; int stat_C, stat_coff; int relu;
+};
+
+struct Plan {
+  int B = 0;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  char* sarena = nullptr;  // InstanceNorm statistics, zeroed at the start of every forward
+  size_t sarena_bytes = 0;
+  std::vector<UmmaConv*> convs;
+  std::map<std::string, TapRec> taps;
+  // staging for ap_netg_forward_host
+  float* h_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* h_out = nullptr;
+  ~Plan() {
+    for (UmmaConv* c : convs) umma_conv_destroy(c);
+    if (arena) cudaFree(arena);
+    if (sarena) cudaFree(sarena);
+    for (float* p : h_in) if (p) cudaFree(p);
+    if (h_out) cudaFree(h_out);
+  }
+};
+
+}  // namespace ap
+
+using namespace ap;
+
+struct ap_netg {
+  int onc = 1, prec = 0, device = 0;
+  bool loaded = false;
+  std::map<std::string, LayerW> w;
+  float* w_stem = nullptr;   // fused stems [49][3][160]
+  float* w_out = nullptr;    // [onc][49][64]
+  float* b_merge = nullptr;  // [256]
+  float* b_out = nullptr;    // [onc]
+  std::vector<void*> owned;  // every device allocation holding weights
+  std::map<int, Plan*> plans;
+  Plan* last_plan = nullptr;
+  int64_t last_launches = 0;
+};
+
+namespace ap {
+
+enum Phase { PH_SIZE = 0, PH_BUILD = 1, PH_EXEC = 2 };
+
+struct Inputs {
+  const float *input, *land1, *land2, *motion, *flow, *ifmask;
+  float* out;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Runner {
+  ap_netg* h;
+  Plan* pl;
+  Phase ph;
+  cudaStream_t st;
+  size_t off = 0, soff = 0, conv_i = 0;
+
+  void* alloc(size_t bytes) {
+    off = align_up(off, 1024);
+    void* p = (ph == PH_SIZE) ? nullptr : (void*)(pl->arena + off);
+    off += bytes;
+    return p;
+  }
+  double* alloc_stats(size_t n) {
+    soff = align_up(soff, 256);
+    double* p = (ph == PH_SIZE) ? nullptr : (double*)(pl->sarena + soff);
+    soff += n * sizeof(double);
+    return p;
+  }
+  Act act(int B, int H, int W, int C, int pad, int fmt) {
+    Act a;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.pad = pad; a.fmt = fmt;
+    const size_t es = (fmt == FMT_F32) ? 4 : 2;
+    a.p0 = alloc(a.elems() * es);
+    if (fmt == FMT_BF16X2) a.p1 = alloc(a.elems() * es);
+    return a;
+  }
+  Raw raw(int B, int H, int W, int C, bool stats) {
+    Raw r;
+    r.B = B; r.H = H; r.W = W; r.C = C;
+    r.p = (float*)alloc((size_t)B * H * W * C * sizeof(float));
+    r.stats = stats ? alloc_stats((size_t)B * C * 2) : nullptr;
+    return r;
+  }
+  void tap_act(const char* name, const Act& a, int coff, int C) {
+    if (ph != PH_BUILD) return;
+    pl->taps[name] = TapRec{a.B, a.H, a.W, C, a.fmt, a.p0, a.p1, a.C, coff, a.pad, nullptr, 0, 0, 0};
+  }
+  void tap_raw(const char* name, const Raw& r, int coff, int C, int relu) {
+    if (ph != PH_BUILD) return;
+    pl->taps[name] = TapRec{r.B, r.H, r.W, C, FMT_F32, r.p, nullptr, r.C, coff, 0, r.stats, r.C, coff, relu};
+  }
+  void tap_f32(const char* name, const float* p, int B, int H, int W, int C) {
+    if (ph != PH_BUILD) return;
+    pl->taps[name] = TapRec{B, H, W, C, FMT_F32, p, nullptr, C, 0, 0, nullptr, 0, 0, 0};
+  }
+
+  const LayerW& W(const std::string& n) { return h->w.at(n); }
+
+  // A 3x3 / transposed-conv layer on the tensor-core or the CUDA-core path, by handle precision.
+  int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff) {
+    if (h->prec == AP_PREC_FP32_SIMT) {
+      if (ph != PH_EXEC) return AP_OK;
+      SimtConvP p{};
+      p.g = g;
+      p.in = (const float*)in.p0; p.in_nchw = 0; p.in_C = in.C; p.in_coff = in_coff;
+      p.wpk = w.simt;
+      p.out = out.p; p.out_C = out.C; p.out_coff = out_coff;
+      p.stats = out.stats; p.stat_C = out.C; p.stat_coff = out_coff;
+      return launch_conv_simt(p, st);
+    }
+    if (ph == PH_SIZE) return AP_OK;
+    if (ph == PH_BUILD) {
+      UmmaConv* c = nullptr;
+      AP_TRY(umma_conv_create(&c, g, in, in_coff, w.hi, w.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C,
+                              out_coff, out.stats, out.C, out_coff));
+      pl->convs.push_back(c);
+      return AP_OK;
+    }
+    return umma_conv_launch(pl->convs.at(conv_i++), st);
+  }
+  // thin CUDA-core layers (stems, landmark branch): fp32 input, NCHW or NHWC
+  int conv_thin(const ConvGeom& g, const float* in, int nchw, int in_C, const float* wpk, const Raw& out) {
+    if (ph != PH_EXEC) return AP_OK;
+    SimtConvP p{};
+    p.g = g;
+    p.in = in; p.in_nchw = nchw; p.in_C = in_C; p.in_coff = 0;
+    p.wpk = wpk;
+    p.out = out.p; p.out_C = out.C; p.out_coff = 0;
+    p.stats = out.stats; p.stat_C = out.C; p.stat_coff = 0;
+    return launch_conv_simt(p, st);
+  }
+  int apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias = nullptr,
+            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr) {
+    if (ph != PH_EXEC) return AP_OK;
+    ApplyP p{};
+    p.raw = r.p; p.raw_C = r.C; p.raw_coff = rcoff;
+    p.stats = r.stats; p.stat_C = r.C; p.stat_coff = rcoff;
+    p.bias = bias;
+    if (r2) { p.raw2 = r2->p; p.raw2_C = r2->C; p.raw2_coff = 0; p.stats2 = r2->stats; p.stat2_C = r2->C; p.stat2_coff = 0; }
+    p.res_in = res_in; p.res_out = res_out;
+    p.relu = relu;
+    p.B = r.B; p.H = r.H; p.W = r.W; p.C = C;
+    if (dst) { p.fmt = dst->fmt; p.d0 = dst->p0; p.d1 = dst->p1; p.dC = dst->C; p.dcoff = dcoff; p.dpad = dst->pad; }
+    else p.fmt = -1;
+    p.halo_reflect = halo;
+    return launch_apply(p, st);
+  }
+  int warp(const Raw& r, int rcoff, int C, int level, const Inputs& in, const Act& dst, int dcoff) {
+    if (ph != PH_EXEC) return AP_OK;
+    WarpP p{};
+    p.raw = r.p; p.raw_C = r.C; p.raw_coff = rcoff;
+    p.stats = r.stats; p.stat_C = r.C; p.stat_coff = rcoff;
+    p.motion = in.motion; p.flow = in.flow; p.ifmask = in.ifmask;
+    p.B = r.B; p.S = r.H; p.C = C; p.level = level;
+    p.fmt = dst.fmt; p.d0 = dst.p0; p.d1 = dst.p1; p.dC = dst.C; p.dcoff = dcoff; p.dpad = dst.pad;
+    return launch_warp(p, st);
+  }
+
+  int run(const Inputs& in);
+};
+
+static ConvGeom geom_conv(int B, int Hin, int Cin, int Cout, int k, int stride, int pad, int reflect) {
+  ConvGeom g{};
+  g.B = B; g.Hin = Hin; g.Win = Hin; g.Cin = Cin;
+  g.Hv = Hin / stride; g.Wv = Hin / stride;
+  g.stride = stride; g.reflect = reflect; g.Cout = Cout;
+  g.os = 1; g.py = 0; g.px = 0; g.Hout = g.Hv; g.Wout = g.Wv;
+  g.taps = make_taps_conv(k, pad, 0);
+  return g;
+}
+static ConvGeom geom_convT_phase(int B, int Hin, int Cin, int Cout, int py, int px) {
+  ConvGeom g{};
+  g.B = B; g.Hin = Hin; g.Win = Hin; g.Cin = Cin;
+  g.Hv = Hin; g.Wv = Hin;
+  g.stride = 1; g.reflect = 0; g.Cout = Cout;
+  g.os = 2; g.py = py; g.px = px; g.Hout = 2 * Hin; g.Wout = 2 * Hin;
+  g.taps = make_taps_convT_phase(py, px);
+  return g;
+}
+
+int Runner::run(const Inputs& in) {
+  const int B = pl->B;
+  const int prec = h->prec;
+  const int afmt = (prec == AP_PREC_FP32X3) ? FMT_BF16X2 : (prec == AP_PREC_BF16 ? FMT_BF16 : FMT_F32);
+  const int hp = (prec == AP_PREC_FP32_SIMT) ? 0 : 1;  // halo of reflect-padded tensor-core inputs
+
+  if (ph == PH_EXEC && pl->sarena_bytes) AP_CUDA(cudaMemsetAsync(pl->sarena, 0, pl->sarena_bytes, st));
+
+  // ---- three 7x7 stems fused into one Cout=160 problem on the photo (networks.py:1218-1243) ----
+  Raw stem = raw(B, 256, 256, 160, true);
+  AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
+  tap_raw("tri00", stem, 0, 32, 1);
+  tap_raw("tri10", stem, 32, 64, 1);
+  tap_raw("tri20", stem, 96, 64, 1);
+
+  // ---- branch 1: warp L0 -> tri01 -> tri02 ----
+  Act W0 = act(B, 256, 256, 64, 0, afmt);
+  AP_TRY(warp(stem, 0, 32, 0, in, W0, 0));
+  tap_act("warp0", W0, 0, 64);
+  Raw r01 = raw(B, 128, 128, 128, true);
+  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), W0, 0, W("model_tri01.0"), r01, 0));
+  tap_raw("tri01", r01, 0, 128, 1);
+  Act A01 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(apply(r01, 0, 128, 1, &A01, 0, 0));
+  Raw r02 = raw(B, 64, 64, 256, true);
+  AP_TRY(conv(geom_conv(B, 128, 128, 256, 3, 2, 1, 0), A01, 0, W("model_tri02.0"), r02, 0));
+  tap_raw("tri02", r02, 0, 256, 1);
+  Act MI = act(B, 64, 64, 768, 0, afmt);  // cat[x1, x2, x3] (networks.py:1330) as channel offsets
+  AP_TRY(apply(r02, 0, 256, 1, &MI, 0, 0));
+
+  // ---- stems of branches 2 and 3, normalised once: T12 = [tri10 | tri20] ----
+  Act T12 = act(B, 256, 256, 128, 0, afmt);
+  AP_TRY(apply(stem, 32, 128, 1, &T12, 0, 0));
+
+  // ---- branch 2: tri11 -> warp L1 -> tri12 ----
+  Raw r11 = raw(B, 128, 128, 64, true);
+  AP_TRY(conv(geom_conv(B, 256, 64, 64, 3, 2, 1, 0), T12, 0, W("model_tri11.0"), r11, 0));
+  tap_raw("tri11", r11, 0, 64, 1);
+  Act W1 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(warp(r11, 0, 64, 1, in, W1, 0));
+  tap_act("warp1", W1, 0, 128);
+  Raw r12 = raw(B, 64, 64, 256, true);
+  AP_TRY(conv(geom_conv(B, 128, 128, 256, 3, 2, 1, 0), W1, 0, W("model_tri12.0"), r12, 0));
+  tap_raw("tri12", r12, 0, 256, 1);
+  AP_TRY(apply(r12, 0, 256, 1, &MI, 256, 0));
+
+  // ---- branch 3: tri21 -> tri22 -> warp L2 ----
+  Raw r21 = raw(B, 128, 128, 128, true);
+  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), T12, 64, W("model_tri21.0"), r21, 0));
+  tap_raw("tri21", r21, 0, 128, 1);
+  Act A21 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(apply(r21, 0, 128, 1, &A21, 0, 0));
+  Raw r22 = raw(B, 64, 64, 128, true);
+  AP_TRY(conv(geom_conv(B, 128, 128, 128, 3, 2, 1, 0), A21, 0, W("model_tri22.0"), r22, 0));
+  tap_raw("tri22", r22, 0, 128, 1);
+  AP_TRY(warp(r22, 0, 128, 2, in, MI, 512));
+  tap_act("warp2", MI, 512, 256);
+
+  // ---- merge: Conv3 768->256, zero pad, bias kept, no norm (networks.py:1251,1330) ----
+  Raw rM = raw(B, 64, 64, 256, false);
+  AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0));
+  Act XL = act(B, 64, 64, 288, hp, afmt);  // cat[x, l1, l2] (networks.py:1335)
+  Act X = act(B, 64, 64, 256, hp, afmt);
+  Act T = act(B, 64, 64, 256, hp, afmt);
+  Act D0 = act(B, 64, 64, 256, 0, afmt);   // decoder input
+  float* xres[10];
+  for (int i = 0; i < 10; ++i) xres[i] = (float*)alloc((size_t)B * 64 * 64 * 256 * sizeof(float));
+  AP_TRY(apply(rM, 0, 256, 0, &XL, 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
+  tap_f32("merge", xres[0], B, 64, 64, 256);
+
+  // ---- landmark branch, twice (networks.py:1280-1282, 1331-1332) ----
+  for (int li = 0; li < 2; ++li) {
+    const float* land = li == 0 ? in.land1 : in.land2;
+    Raw rl0 = raw(B, 256, 256, 8, true);
+    AP_TRY(conv_thin(geom_conv(B, 256, 1, 8, 3, 1, 1, 0), land, 1, 1, W("model_landmark_trans.0").simt, rl0));
+    Act L0 = act(B, 256, 256, 8, 0, FMT_F32);
+    AP_TRY(apply(rl0, 0, 8, 1, &L0, 0, 0));
+    Raw rl1 = raw(B, 128, 128, 16, true);
+    AP_TRY(conv_thin(geom_conv(B, 256, 8, 16, 3, 2, 1, 0), (const float*)L0.p0, 0, 8, W("model_landmark_trans.3").simt, rl1));
+    Act L1 = act(B, 128, 128, 16, 0, FMT_F32);
+    AP_TRY(apply(rl1, 0, 16, 1, &L1, 0, 0));
+    Raw rl2 = raw(B, 64, 64, 16, true);
+    AP_TRY(conv_thin(geom_conv(B, 128, 16, 16, 3, 2, 1, 0), (const float*)L1.p0, 0, 16, W("model_landmark_trans.6").simt, rl2));
+    AP_TRY(apply(rl2, 0, 16, 0, &XL, 256 + 16 * li, 1));
+    tap_act(li == 0 ? "land1" : "land2", XL, 256 + 16 * li, 16);
+  }
+
+  // ---- 9 residual blocks (networks.py:1333-1337, 2303-2421) ----
+  for (int i = 0; i < 9; ++i) {
+    const std::string b = "model2." + std::to_string(i);
+    const bool b2 = (i % 3) == 0;
+    const Act& src = b2 ? XL : X;
+    const int cin = b2 ? 288 : 256;
+    const Act* dst = (i == 8) ? &D0 : (((i + 1) % 3 == 0) ? &XL : &X);
+    const int dst_halo = (i == 8) ? 0 : 1;
+    Raw rs;
+    if (b2) {
+      rs = raw(B, 64, 64, 256, true);
+      AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0));
+    }
+    Raw r1 = raw(B, 64, 64, 256, true);
+    AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 1), src, 0, W(b + ".conv_block.1"), r1, 0));
+    AP_TRY(apply(r1, 0, 256, 1, &T, 0, 1));
+    Raw r2 = raw(B, 64, 64, 256, true);
+    AP_TRY(conv(geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, 0, W(b + ".conv_block.5"), r2, 0));
+    if (b2) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1]));
+    else AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, xres[i], xres[i + 1]));
+    const std::string tn = "block" + std::to_string(i);
+    tap_f32(tn.c_str(), xres[i + 1], B, 64, 64, 256);
+  }
+
+  // ---- decoder (networks.py:1268-1279): two ConvT as 4 output phases each, then the 7x7 output conv ----
+  Raw ru0 = raw(B, 128, 128, 128, true);
+  for (int ph_ = 0; ph_ < 4; ++ph_)
+    AP_TRY(conv(geom_convT_phase(B, 64, 256, 128, ph_ >> 1, ph_ & 1), D0, 0, W("model3.0"), ru0, 0));
+  tap_raw("up0", ru0, 0, 128, 1);
+  Act U0 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(apply(ru0, 0, 128, 1, &U0, 0, 0));
+  Raw ru1 = raw(B, 256, 256, 64, true);
+  for (int ph_ = 0; ph_ < 4; ++ph_)
+    AP_TRY(conv(geom_convT_phase(B, 128, 128, 64, ph_ >> 1, ph_ & 1), U0, 0, W("model3.3"), ru1, 0));
+  tap_raw("up1", ru1, 0, 64, 1);
+  if (ph == PH_EXEC) {
+    OutConvP p{};
+    p.raw = ru1.p; p.stats = ru1.stats; p.w = h->w_out; p.bias = h->b_out; p.out = in.out; p.B = B; p.onc = h->onc;
+    AP_TRY(launch_out_conv(p, st));
+  }
+  return AP_OK;
+}
+
+static int get_plan(ap_netg* h, int B, Plan** out) {
+  auto it = h->plans.find(B);
+  if (it != h->plans.end()) { *out = it->second; return AP_OK; }
+  Plan* pl = new Plan();
+  pl->B = B;
+  Inputs none{};
+  Runner rs{h, pl, PH_SIZE, nullptr};
+  int rc = rs.run(none);
+  if (rc != AP_OK) { delete pl; return rc; }
+  pl->arena_bytes = align_up(rs.off, 1024);
+  pl->sarena_bytes = align_up(rs.soff, 256);
+  if (cudaMalloc(&pl->arena, pl->arena_bytes) != cudaSuccess || cudaMalloc(&pl->sarena, pl->sarena_bytes) != cudaSuccess) {
+    set_error("workspace allocation of %zu bytes for B=%d failed: %s", pl->arena_bytes, B,
+              cudaGetErrorString(cudaGetLastError()));
+    delete pl;
+    return AP_ERR_CUDA;
+  }
+  // halos of zero-padded / never-written regions must read as zero
+  if (cudaMemset(pl->arena, 0, pl->arena_bytes) != cudaSuccess) { delete pl; set_error("memset failed"); return AP_ERR_CUDA; }
+  Runner rb{h, pl, PH_BUILD, nullptr};
+  rc = rb.run(none);
+  if (rc != AP_OK) { delete pl; return rc; }
+  h->plans[B] = pl;
+  *out = pl;
+  return AP_OK;
+}
+
+}  // namespace ap
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* ap_last_error(void) { return ap::g_err; }
+const char* ap_version(void) { return "apnetg 0.1 sm_100a"; }
+
+int ap_netg_create(ap_netg** handle, int output_nc, int precision, int device) {
+  AP_REQUIRE(handle != nullptr, AP_ERR_INVALID, "null handle pointer");
+  AP_REQUIRE(output_nc == 1 || output_nc == 3, AP_ERR_UNSUPPORTED, "output_nc=%d not supported (1 or 3)", output_nc);
+  AP_REQUIRE(precision >= 0 && precision <= 2, AP_ERR_INVALID, "precision=%d", precision);
+  int ndev = 0;
+  AP_CUDA(cudaGetDeviceCount(&ndev));
+  AP_REQUIRE(device >= 0 && device < ndev, AP_ERR_INVALID, "device %d of %d", device, ndev);
+  AP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AP_CUDA(cudaGetDeviceProperties(&prop, device));
+  AP_REQUIRE(prop.major == 10, AP_ERR_UNSUPPORTED, "libapnetg is built for sm_100a only; device %d is sm_%d%d", device,
+             prop.major, prop.minor);
+  if (precision != AP_PREC_FP32_SIMT) AP_TRY(umma_init());
+  ap_netg* h = new ap_netg();
+  h->onc = output_nc; h->prec = precision; h->device = device;
+  *handle = h;
+  return AP_OK;
+}
+
+static void free_weights(ap_netg* h) {
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->w.clear();
+  h->w_stem = h->w_out = h->b_merge = h->b_out = nullptr;
+  h->loaded = false;
+}
+
+int ap_netg_destroy(ap_netg* h) {
+  if (!h) return AP_OK;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->plans) delete kv.second;
+  free_weights(h);
+  delete h;
+  return AP_OK;
+}
+
+int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const float* const* ptrs, const int64_t* shapes,
+                         int on_device, void* cuda_stream) {
+  AP_REQUIRE(h && names && ptrs && shapes, AP_ERR_INVALID, "null argument");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  std::map<std::string, int> idx;
+  for (int i = 0; i < n; ++i) idx[names[i]] = i;
+  const std::vector<LayerSpec> specs = layer_specs(h->onc);
+  AP_REQUIRE(n == (int)specs.size() * 2, AP_ERR_INVALID, "state_dict has %d tensors, expected %d", n, (int)specs.size() * 2);
+  // strict key / shape check before touching anything (load_state_dict(strict=True) semantics)
+  for (const LayerSpec& s : specs) {
+    auto wi = idx.find(s.name + ".weight"), bi = idx.find(s.name + ".bias");
+    AP_REQUIRE(wi != idx.end() && bi != idx.end(), AP_ERR_INVALID, "missing key %s.weight/.bias", s.name.c_str());
+    const int64_t* ws = shapes + 4 * wi->second;
+    const int64_t d0 = s.transposed ? s.cin : s.cout, d1 = s.transposed ? s.cout : s.cin;
+    AP_REQUIRE(ws[0] == d0 && ws[1] == d1 && ws[2] == s.k && ws[3] == s.k, AP_ERR_INVALID,
+               "size mismatch for %s.weight: got [%lld,%lld,%lld,%lld], expected [%lld,%lld,%d,%d]", s.name.c_str(),
+               (long long)ws[0], (long long)ws[1], (long long)ws[2], (long long)ws[3], (long long)d0, (long long)d1, s.k, s.k);
+    AP_REQUIRE(shapes[4 * bi->second] == s.cout, AP_ERR_INVALID, "size mismatch for %s.bias", s.name.c_str());
+  }
+  free_weights(h);
+  auto dalloc = [&](size_t bytes, void** p) -> int {
+    AP_CUDA(cudaMalloc(p, bytes));
+    h->owned.push_back(*p);
+    return AP_OK;
+  };
+  std::vector<void*> staging;
+  auto dev_src = [&](const float* src, size_t elems, const float** out) -> int {
+    if (on_device) { *out = src; return AP_OK; }
+    void* d = nullptr;
+    AP_CUDA(cudaMalloc(&d, elems * sizeof(float)));
+    staging.push_back(d);
+    AP_CUDA(cudaMemcpyAsync(d, src, elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    *out = (const float*)d;
+    return AP_OK;
+  };
+  int rc = AP_OK;
+  AP_TRY(dalloc((size_t)49 * 3 * 160 * 4, (void**)&h->w_stem));
+  AP_TRY(dalloc((size_t)h->onc * 49 * 64 * 4, (void**)&h->w_out));
+  AP_TRY(dalloc(256 * 4, (void**)&h->b_merge));
+  AP_TRY(dalloc(h->onc * 4, (void**)&h->b_out));
+  for (const LayerSpec& s : specs) {
+    const size_t elems = (size_t)s.cout * s.cin * s.k * s.k;
+    const float* src = nullptr;
+    rc = dev_src(ptrs[idx[s.name + ".weight"]], elems, &src);
+    if (rc != AP_OK) break;
+    if (s.name == "model_tri00.1") rc = launch_pack_weights(src, 32, 3, 7, 0, h->w_stem, 160, 0, nullptr, nullptr, st);
+    else if (s.name == "model_tri10.1") rc = launch_pack_weights(src, 64, 3, 7, 0, h->w_stem, 160, 32, nullptr, nullptr, st);
+    else if (s.name == "model_tri20.1") rc = launch_pack_weights(src, 64, 3, 7, 0, h->w_stem, 160, 96, nullptr, nullptr, st);
+    else if (s.name == "model3.7") rc = launch_pack_out_weights(src, h->onc, h->w_out, st);
+    else {
+      LayerW lw;
+      lw.cout = s.cout; lw.cin = s.cin; lw.k = s.k;
+      const bool thin = s.name.rfind("model_landmark_trans", 0) == 0;
+      const bool simt = thin || h->prec == AP_PREC_FP32_SIMT;
+      if (simt) rc = dalloc(elems * 4, (void**)&lw.simt);
+      if (rc == AP_OK && !simt) rc = dalloc(elems * 2, (void**)&lw.hi);
+      if (rc == AP_OK && !simt && h->prec == AP_PREC_FP32X3) rc = dalloc(elems * 2, (void**)&lw.lo);
+      if (rc == AP_OK)
+        rc = launch_pack_weights(src, s.cout, s.cin, s.k, s.transposed ? 1 : 0, lw.simt, s.cout, 0, lw.hi, lw.lo, st);
+      h->w[s.name] = lw;
+    }
+    if (rc != AP_OK) break;
+    const float* bsrc = nullptr;
+    if (s.name == "model_tri_merge" || s.name == "model3.7") {
+      // the only two biases that reach the output (every other conv feeds an affine-less InstanceNorm)
+      float* dst = s.name == "model3.7" ? h->b_out : h->b_merge;
+      rc = dev_src(ptrs[idx[s.name + ".bias"]], s.cout, &bsrc);
+      if (rc == AP_OK && cudaMemcpyAsync(dst, bsrc, s.cout * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("bias copy failed");
+        rc = AP_ERR_CUDA;
+      }
+      if (rc != AP_OK) break;
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (void* p : staging) cudaFree(p);
+  if (rc != AP_OK) { free_weights(h); return rc; }
+  if (e != cudaSuccess) { set_error("weight packing failed: %s", cudaGetErrorString(e)); free_weights(h); return AP_ERR_CUDA; }
+  // plans hold tensor maps that point at the old weight buffers
+  for (auto& kv : h->plans) delete kv.second;
+  h->plans.clear();
+  h->last_plan = nullptr;
+  h->loaded = true;
+  return AP_OK;
+}
+
+int ap_netg_workspace_bytes(ap_netg* h, int B, size_t* bytes) {
+  AP_REQUIRE(h && bytes && B >= 1, AP_ERR_INVALID, "bad argument");
+  Plan pl;
+  pl.B = B;
+  Inputs none{};
+  Runner rs{h, &pl, PH_SIZE, nullptr};
+  // SIZE phase never dereferences weights
+  AP_REQUIRE(h->loaded, AP_ERR_STATE, "load_weights must be called before workspace_bytes");
+  AP_TRY(rs.run(none));
+  *bytes = align_up(rs.off, 1024) + align_up(rs.soff, 256);
+  return AP_OK;
+}
+
+int ap_netg_forward(ap_netg* h, int B, const float* input, const float* land1, const float* land2, const float* motion,
+                    const float* flow, const float* ifmask, float* out, void* cuda_stream) {
+  AP_REQUIRE(h != nullptr, AP_ERR_INVALID, "null handle");
+  AP_REQUIRE(h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1, AP_ERR_INVALID, "B=%d", B);
+  AP_REQUIRE(input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "null tensor pointer");
+  AP_CUDA(cudaSetDevice(h->device));
+  Plan* pl = nullptr;
+  AP_TRY(get_plan(h, B, &pl));
+  const int64_t before = launches_get();
+  Inputs in{input, land1, land2, motion, flow, ifmask, out};
+  Runner rx{h, pl, PH_EXEC, (cudaStream_t)cuda_stream};
+  AP_TRY(rx.run(in));
+  h->last_launches = launches_get() - before;
+  h->last_plan = pl;
+  return AP_OK;
+}
+
+int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* land1, const float* land2,
+                         const float* motion, const float* flow, const float* ifmask, float* out, void* cuda_stream) {
+  AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1 && input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "bad argument");
+  AP_CUDA(cudaSetDevice(h->device));
+  Plan* pl = nullptr;
+  AP_TRY(get_plan(h, B, &pl));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t px = (size_t)B * 256 * 256;
+  const size_t sz[6] = {px * 3, px, px, px * 2, px * 2, px};
+  const float* src[6] = {input, land1, land2, motion, flow, ifmask};
+  for (int i = 0; i < 6; ++i) {
+    if (!pl->h_in[i]) AP_CUDA(cudaMalloc(&pl->h_in[i], sz[i] * sizeof(float)));
+    AP_CUDA(cudaMemcpyAsync(pl->h_in[i], src[i], sz[i] * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (!pl->h_out) AP_CUDA(cudaMalloc(&pl->h_out, px * h->onc * sizeof(float)));
+  AP_TRY(ap_netg_forward(h, B, pl->h_in[0], pl->h_in[1], pl->h_in[2], pl->h_in[3], pl->h_in[4], pl->h_in[5], pl->h_out, st));
+  AP_CUDA(cudaMemcpyAsync(out, pl->h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, st));
+  AP_CUDA(cudaStreamSynchronize(st));
+  return AP_OK;
+}
+
+int ap_netg_last_launch_count(ap_netg* h, int64_t* count) {
+  AP_REQUIRE(h && count, AP_ERR_INVALID, "null argument");
+  *count = h->last_launches;
+  return AP_OK;
+}
+
+int ap_netg_debug_read(ap_netg* h, const char* tap, float* dst, size_t cap, int64_t* shape4, void* cuda_stream) {
+  AP_REQUIRE(h && tap && dst, AP_ERR_INVALID, "null argument");
+  AP_REQUIRE(h->last_plan != nullptr, AP_ERR_STATE, "debug_read before any forward");
+  auto it = h->last_plan->taps.find(tap);
+  AP_REQUIRE(it != h->last_plan->taps.end(), AP_ERR_INVALID, "unknown tap '%s'", tap);
+  const TapRec& t = it->second;
+  const size_t need = (size_t)t.B * t.C * t.H * t.W;
+  AP_REQUIRE(cap >= need, AP_ERR_INVALID, "tap '%s' needs %zu elements, buffer has %zu", tap, need, cap);
+  if (shape4) { shape4[0] = t.B; shape4[1] = t.C; shape4[2] = t.H; shape4[3] = t.W; }
+  AP_CUDA(cudaSetDevice(h->device));
+  ReadP p{t.B, t.H, t.W, t.C, t.fmt, t.p0, t.p1, t.sC, t.scoff, t.spad, t.stats, t.stat_C, t.stat_coff, t.relu, dst};
+  return launch_read(p, (cudaStream_t)cuda_stream);
+}
+
+int ap_conv2d_debug(int impl, int device, int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad,
+                    int pad_mode, int transposed, const float* x, const float* w, float* y, double* stats,
+                    void* cuda_stream) {
+  AP_REQUIRE(x && w && y, AP_ERR_INVALID, "null argument");
+  AP_REQUIRE(H == W, AP_ERR_UNSUPPORTED, "square inputs only");
+  AP_REQUIRE(impl >= 0 && impl <= 2, AP_ERR_INVALID, "impl=%d", impl);
+  AP_REQUIRE(!transposed || (ksize == 3 && stride == 2 && pad == 1), AP_ERR_UNSUPPORTED, "transposed: k3 s2 p1 op1 only");
+  AP_REQUIRE(impl == AP_PREC_FP32_SIMT || (ksize == 3 && pad == 1), AP_ERR_UNSUPPORTED, "tcgen05 path: 3x3 pad 1 only");
+  AP_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool tc = impl != AP_PREC_FP32_SIMT;
+  if (tc) AP_TRY(umma_init());
+  const int Ho = transposed ? 2 * H : H / stride;
+  Act in;
+  in.B = B; in.H = H; in.W = W; in.C = Cin;
+  in.pad = (tc && pad_mode == 1) ? 1 : 0;
+  in.fmt = impl == AP_PREC_FP32X3 ? FMT_BF16X2 : (impl == AP_PREC_BF16 ? FMT_BF16 : FMT_F32);
+  const size_t es = in.fmt == FMT_F32 ? 4 : 2;
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes, void** p) -> int {
+    AP_CUDA(cudaMalloc(p, bytes));
+    tmp.push_back(*p);
+    AP_CUDA(cudaMemsetAsync(*p, 0, bytes, st));
+    return AP_OK;
+  };
+  int rc = dalloc(in.elems() * es, &in.p0);
+  if (rc == AP_OK && in.fmt == FMT_BF16X2) rc = dalloc(in.elems() * es, &in.p1);
+  const size_t welems = (size_t)Cout * Cin * ksize * ksize;
+  LayerW lw;
+  if (rc == AP_OK && !tc) rc = dalloc(welems * 4, (void**)&lw.simt);
+  if (rc == AP_OK && tc) rc = dalloc(welems * 2, (void**)&lw.hi);
+  if (rc == AP_OK && impl == AP_PREC_FP32X3) rc = dalloc(welems * 2, (void**)&lw.lo);
+  Raw out;
+  out.B = B; out.H = Ho; out.W = Ho; out.C = Cout;
+  if (rc == AP_OK) rc = dalloc((size_t)B * Ho * Ho * Cout * 4, (void**)&out.p);
+  if (rc == AP_OK) rc = dalloc((size_t)B * Cout * 2 * 8, (void**)&out.stats);
+  std::vector<UmmaConv*> convs;
+  if (rc == AP_OK) rc = launch_nchw_to_act(x, in, st);
+  if (rc == AP_OK) rc = launch_pack_weights(w, Cout, Cin, ksize, transposed, lw.simt, Cout, 0, lw.hi, lw.lo, st);
+  const int nph = transposed ? 4 : 1;
+  for (int ph = 0; ph < nph && rc == AP_OK; ++ph) {
+    ConvGeom g = transposed ? geom_convT_phase(B, H, Cin, Cout, ph >> 1, ph & 1)
+                            : geom_conv(B, H, Cin, Cout, ksize, stride, pad, pad_mode);
+    if (!tc) {
+      SimtConvP p{};
+      p.g = g; p.in = (const float*)in.p0; p.in_nchw = 0; p.in_C = Cin; p.in_coff = 0; p.wpk = lw.simt;
+      p.out = out.p; p.out_C = Cout; p.out_coff = 0; p.stats = out.stats; p.stat_C = Cout; p.stat_coff = 0;
+      rc = launch_conv_simt(p, st);
+    } else {
+      UmmaConv* c = nullptr;
+      rc = umma_conv_create(&c, g, in, 0, lw.hi, lw.lo, impl == AP_PREC_FP32X3 ? 3 : 1, out.p, Cout, 0, out.stats, Cout, 0);
+      if (rc == AP_OK) { convs.push_back(c); rc = umma_conv_launch(c, st); }
+    }
+  }
+  if (rc == AP_OK) {
+    ReadP rp{B, Ho, Ho, Cout, FMT_F32, out.p, nullptr, Cout, 0, 0, nullptr, 0, 0, 0, y};
+    rc = launch_read(rp, st);
+  }
+  if (rc == AP_OK && stats &&
+      cudaMemcpyAsync(stats, out.stats, (size_t)B * Cout * 2 * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    set_error("stats copy failed");
+    rc = AP_ERR_CUDA;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (UmmaConv* c : convs) umma_conv_destroy(c);
+  for (void* p : tmp) cudaFree(p);
+  if (rc == AP_OK && e != cudaSuccess) { set_error("conv2d_debug: %s", cudaGetErrorString(e)); rc = AP_ERR_CUDA; }
+  return rc;
+}
+
+}  // extern "C"

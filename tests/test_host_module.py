@@ -1,0 +1,97 @@
+"""CPU: the host-side mirror keeps the reference generator's interface (constructor, state_dict layout,
+error behaviour) -- Module2/models/networks.py:123-201,1190-1340."""
+import functools
+import inspect
+
+import pytest
+import torch
+import torch.nn as nn
+
+import animateportrait_b200 as ap
+from oracle import netg_oracle as O
+
+
+def _make(onc=1, **kw):
+    return ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [], div=3, disp=3, **kw)
+
+
+@pytest.mark.parametrize("onc", [1, 3])
+def test_state_dict_layout_is_the_reference_checkpoint_layout(onc):
+    net = _make(onc)
+    sd = net.state_dict()
+    spec = O.state_dict_spec(onc)
+    assert list(sd.keys()) == list(spec.keys())  # same keys, same ORDER, no 'module.' prefix
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # a checkpoint written by the reference (torch.save(net.state_dict())) loads strictly
+    res = net.load_state_dict(O.make_state_dict(onc, seed=1))
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_load_networks_style_key_walk():
+    # BaseModel.__patch_instance_norm_state_dict walks getattr(module, part) along every key (base_model.py:165-177)
+    net = _make(1)
+    for key in net.state_dict():
+        obj = net
+        for part in key.split(".")[:-1]:
+            obj = getattr(obj, part)
+        assert hasattr(obj, key.split(".")[-1])
+
+
+def test_init_weights_is_normal_0_02_and_zero_bias():
+    torch.manual_seed(0)
+    net = _make(1)
+    w = net.model2[1].conv_block[1].weight
+    assert abs(w.std().item() - 0.02) < 1e-3 and abs(w.mean().item()) < 1e-3
+    assert all(float(p.abs().sum()) == 0.0 for n, p in net.named_parameters() if n.endswith(".bias"))
+
+
+def test_define_g_signature_matches_reference():
+    params = list(inspect.signature(ap.define_G).parameters)
+    assert params[:15] == ["input_nc", "output_nc", "ngf", "netG", "norm", "use_dropout", "init_type", "init_gain",
+                           "gpu_ids", "model0_res", "model1_res", "extra_channel", "div", "disp", "regarch"]
+    fwd = list(inspect.signature(ap.ResnetConditionTriGenerator32_full_ifw.forward).parameters)
+    assert fwd == ["self", "input", "land1", "land2", "motion", "flow", "ifmask"]
+
+
+def test_unsupported_configurations_raise_like_the_reference():
+    with pytest.raises(NotImplementedError):
+        ap.define_G(3, 1, 64, "resnet_9blocks", "instance")
+    with pytest.raises(NotImplementedError):
+        ap.define_G(3, 1, 64, ap.NETG_NAME, "batch", div=3, disp=3)
+    with pytest.raises(NotImplementedError):
+        ap.define_G(3, 2, 64, ap.NETG_NAME, "instance", div=3, disp=3)
+    with pytest.raises(NotImplementedError):
+        ap.define_G(3, 1, 32, ap.NETG_NAME, "instance", div=3, disp=3)
+    with pytest.raises(NotImplementedError):
+        ap.define_G(3, 1, 64, ap.NETG_NAME, "instance", div=3, disp=1)  # reference default disp=1: other block layout
+    with pytest.raises(NotImplementedError):
+        ap.define_G(3, 1, 64, ap.NETG_NAME, "instance", div=3, disp=3, init_type="xavier")
+
+
+def test_no_cpu_fallback():
+    net = _make(1)
+    x, l1, l2, motion, flow, ifmask = O.make_inputs(1, seed=1)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        net(x, l1, l2, motion, flow, ifmask)
+    with pytest.raises(RuntimeError):
+        net.model2[0](x)  # parameter holders are not executable
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    root = os.path.dirname(os.path.abspath(ap.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_install_patches_a_networks_namespace():
+    import types
+    fake = types.SimpleNamespace(ResnetConditionTriGenerator32_full_ifw=None)
+    ap.install(fake, precision="bf16")
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    net = fake.ResnetConditionTriGenerator32_full_ifw(3, 1, 64, norm_layer=norm, use_dropout=False, n_blocks=9, div=3, disp=3)
+    assert isinstance(net, ap.ResnetConditionTriGenerator32_full_ifw) and net.precision == "bf16"
