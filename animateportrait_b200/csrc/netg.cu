@@ -97,8 +97,16 @@ struct Plan {
 
 using namespace ap;
 
+constexpr int AP_NCLASS = 7;
+enum { CL_STEM = 0, CL_LAND = 1, CL_TRUNK = 2, CL_STRIDED = 3, CL_APPLY = 4, CL_WARP = 5, CL_OUT = 6 };
+
 struct ap_netg {
   int onc = 1, prec = 0, device = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;      // ev[0] = start, ev[i+1] = after launch i
+  std::vector<int> ev_class;        // class of launch i
+  std::vector<double> ev_flops;
+  size_t ev_used = 0;
   bool loaded = false;
   std::map<std::string, LayerW> w;
   float* w_stem = nullptr;   // fused stems [49][3][160]
@@ -171,6 +179,24 @@ struct Runner {
 
   const LayerW& W(const std::string& n) { return h->w.at(n); }
 
+  // profiling: one event after every launch (stream order => consecutive differences are kernel times)
+  int mark(int cls, double flops) {
+    if (ph != PH_EXEC || !h->profiling) return AP_OK;
+    if (h->ev_used + 1 >= h->ev.size()) {
+      cudaEvent_t e;
+      AP_CUDA(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+    AP_CUDA(cudaEventRecord(h->ev[h->ev_used + 1], st));
+    h->ev_class.push_back(cls);
+    h->ev_flops.push_back(flops);
+    ++h->ev_used;
+    return AP_OK;
+  }
+  static double conv_flops(const ConvGeom& g) {
+    return 2.0 * g.B * g.Hv * g.Wv * (double)g.Cin * g.Cout * g.taps.n;
+  }
+
   // A 3x3 / transposed-conv layer on the tensor-core or the CUDA-core path, by handle precision.
   int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff) {
     if (h->prec == AP_PREC_FP32_SIMT) {
@@ -181,7 +207,8 @@ struct Runner {
       p.wpk = w.simt;
       p.out = out.p; p.out_C = out.C; p.out_coff = out_coff;
       p.stats = out.stats; p.stat_C = out.C; p.stat_coff = out_coff;
-      return launch_conv_simt(p, st);
+      AP_TRY(launch_conv_simt(p, st));
+      return mark((g.stride == 1 && g.os == 1) ? CL_TRUNK : CL_STRIDED, conv_flops(g));
     }
     if (ph == PH_SIZE) return AP_OK;
     if (ph == PH_BUILD) {
@@ -191,7 +218,8 @@ struct Runner {
       pl->convs.push_back(c);
       return AP_OK;
     }
-    return umma_conv_launch(pl->convs.at(conv_i++), st);
+    AP_TRY(umma_conv_launch(pl->convs.at(conv_i++), st));
+    return mark((g.stride == 1 && g.os == 1) ? CL_TRUNK : CL_STRIDED, conv_flops(g));
   }
   // thin CUDA-core layers (stems, landmark branch): fp32 input, NCHW or NHWC
   int conv_thin(const ConvGeom& g, const float* in, int nchw, int in_C, const float* wpk, const Raw& out) {
@@ -202,7 +230,8 @@ struct Runner {
     p.wpk = wpk;
     p.out = out.p; p.out_C = out.C; p.out_coff = 0;
     p.stats = out.stats; p.stat_C = out.C; p.stat_coff = 0;
-    return launch_conv_simt(p, st);
+    AP_TRY(launch_conv_simt(p, st));
+    return mark(g.taps.n == 49 ? CL_STEM : CL_LAND, conv_flops(g));
   }
   int apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias = nullptr,
             const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr) {
@@ -218,7 +247,8 @@ struct Runner {
     if (dst) { p.fmt = dst->fmt; p.d0 = dst->p0; p.d1 = dst->p1; p.dC = dst->C; p.dcoff = dcoff; p.dpad = dst->pad; }
     else p.fmt = -1;
     p.halo_reflect = halo;
-    return launch_apply(p, st);
+    AP_TRY(launch_apply(p, st));
+    return mark(CL_APPLY, 0.0);
   }
   int warp(const Raw& r, int rcoff, int C, int level, const Inputs& in, const Act& dst, int dcoff) {
     if (ph != PH_EXEC) return AP_OK;
@@ -228,7 +258,8 @@ struct Runner {
     p.motion = in.motion; p.flow = in.flow; p.ifmask = in.ifmask;
     p.B = r.B; p.S = r.H; p.C = C; p.level = level;
     p.fmt = dst.fmt; p.d0 = dst.p0; p.d1 = dst.p1; p.dC = dst.C; p.dcoff = dcoff; p.dpad = dst.pad;
-    return launch_warp(p, st);
+    AP_TRY(launch_warp(p, st));
+    return mark(CL_WARP, 0.0);
   }
 
   int run(const Inputs& in);
@@ -379,6 +410,7 @@ int Runner::run(const Inputs& in) {
     OutConvP p{};
     p.raw = ru1.p; p.stats = ru1.stats; p.w = h->w_out; p.bias = h->b_out; p.out = in.out; p.B = B; p.onc = h->onc;
     AP_TRY(launch_out_conv(p, st));
+    AP_TRY(mark(CL_OUT, 2.0 * B * 256.0 * 256.0 * 64 * 49 * h->onc));
   }
   return AP_OK;
 }
@@ -451,6 +483,7 @@ int ap_netg_destroy(ap_netg* h) {
   if (!h) return AP_OK;
   cudaSetDevice(h->device);
   for (auto& kv : h->plans) delete kv.second;
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   free_weights(h);
   delete h;
   return AP_OK;
@@ -568,6 +601,17 @@ int ap_netg_forward(ap_netg* h, int B, const float* input, const float* land1, c
   const int64_t before = launches_get();
   Inputs in{input, land1, land2, motion, flow, ifmask, out};
   Runner rx{h, pl, PH_EXEC, (cudaStream_t)cuda_stream};
+  if (h->profiling) {
+    if (h->ev.empty()) {
+      cudaEvent_t e;
+      AP_CUDA(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+    h->ev_used = 0;
+    h->ev_class.clear();
+    h->ev_flops.clear();
+    AP_CUDA(cudaEventRecord(h->ev[0], (cudaStream_t)cuda_stream));
+  }
   AP_TRY(rx.run(in));
   h->last_launches = launches_get() - before;
   h->last_plan = pl;
@@ -599,6 +643,32 @@ int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* lan
 int ap_netg_last_launch_count(ap_netg* h, int64_t* count) {
   AP_REQUIRE(h && count, AP_ERR_INVALID, "null argument");
   *count = h->last_launches;
+  return AP_OK;
+}
+
+int ap_netg_set_profiling(ap_netg* h, int enable) {
+  AP_REQUIRE(h != nullptr, AP_ERR_INVALID, "null handle");
+  h->profiling = enable != 0;
+  h->ev_used = 0;
+  h->ev_class.clear();
+  h->ev_flops.clear();
+  return AP_OK;
+}
+
+int ap_netg_get_profile(ap_netg* h, int max_classes, double* ms, int64_t* launches, double* flops, int* n_classes) {
+  AP_REQUIRE(h && ms && launches && flops && n_classes, AP_ERR_INVALID, "null argument");
+  AP_REQUIRE(h->profiling && h->ev_used > 0, AP_ERR_STATE, "no profiled forward recorded");
+  AP_CUDA(cudaSetDevice(h->device));
+  AP_CUDA(cudaEventSynchronize(h->ev[h->ev_used]));
+  const int nc = max_classes < AP_NCLASS ? max_classes : AP_NCLASS;
+  for (int c = 0; c < nc; ++c) { ms[c] = 0.0; launches[c] = 0; flops[c] = 0.0; }
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    float t = 0.f;
+    AP_CUDA(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+    const int c = h->ev_class[i];
+    if (c < nc) { ms[c] += t; launches[c] += 1; flops[c] += h->ev_flops[i]; }
+  }
+  *n_classes = nc;
   return AP_OK;
 }
 

@@ -214,6 +214,18 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
         _capi.check(_capi.lib().ap_netg_last_launch_count(self._handle, C.byref(n)), "ap_netg_last_launch_count")
         return int(n.value)
 
+    PROFILE_CLASSES = ("stem7x7", "landmark", "trunk_conv3x3", "strided_convs", "in_apply", "warp", "out_conv")
+
+    def set_profiling(self, enable: bool) -> None:
+        _capi.check(_capi.lib().ap_netg_set_profiling(self._handle, 1 if enable else 0), "ap_netg_set_profiling")
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        """Per kernel class of the last profiled forward: {'ms', 'launches', 'flops'} (device time, CUDA events)."""
+        n = len(self.PROFILE_CLASSES)
+        ms, la, fl, nc = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)(), C.c_int(0)
+        _capi.check(_capi.lib().ap_netg_get_profile(self._handle, n, ms, la, fl, C.byref(nc)), "ap_netg_get_profile")
+        return {self.PROFILE_CLASSES[i]: {"ms": ms[i], "launches": int(la[i]), "flops": fl[i]} for i in range(nc.value)}
+
     def workspace_bytes(self, B: int) -> int:
         n = C.c_size_t(0)
         _capi.check(_capi.lib().ap_netg_workspace_bytes(self._handle, B, C.byref(n)), "ap_netg_workspace_bytes")

@@ -78,6 +78,16 @@ int ap_netg_forward_host(ap_netg* handle, int B, const float* input, const float
 /* Number of kernels of this library launched by the most recent forward on this handle. */
 int ap_netg_last_launch_count(ap_netg* handle, int64_t* count);
 
+/* Per-kernel-class device timing of the forward (CUDA events on the launch stream, one per launch).
+ * While enabled every forward records events; ap_netg_get_profile synchronises and returns, for the
+ * most recent forward, per class: total milliseconds, launches and algorithmic FLOPs (2*MACs).
+ * Classes: 0 stem7x7 (CUDA cores), 1 landmark convs (CUDA cores), 2 trunk conv 3x3 s1 @64x64,
+ * 3 strided / transposed convs, 4 InstanceNorm apply, 5 double warp, 6 output conv 7x7 + tanh.
+ * Returns the number of classes written (<= max_classes) through *n_classes. */
+int ap_netg_set_profiling(ap_netg* handle, int enable);
+int ap_netg_get_profile(ap_netg* handle, int max_classes, double* ms, int64_t* launches, double* flops,
+                        int* n_classes);
+
 /* Debug/validation: copy a named intermediate of the most recent forward to `dst` as NCHW fp32.
  * Names follow oracle/netg_oracle.py taps: tri00 warp0 tri01 tri02 tri10 tri11 warp1 tri12 tri20 tri21
  * tri22 warp2 merge land1 land2 block0..block8 up0 up1.  `shape4` receives [B,C,H,W]. */

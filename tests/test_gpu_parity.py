@@ -1,0 +1,187 @@
+"""GPU (B200): parity of the CUDA path against the oracle and the committed golden vectors, through the
+C ABI.  fp32 gate: max-abs <= 1e-3 (BASELINE.json north_star); bf16 gate: max-abs <= 0.1, mean-abs <= 0.012
+(measured bf16-pipeline error on the oracle is 6-7e-2 / 8e-3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import animateportrait_b200 as ap
+from oracle import netg_oracle as O
+from tests.golden.make_golden import CASES
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+FP32_TOL = 1e-3
+BF16_MAX, BF16_MEAN = 0.1, 0.012
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _net(onc, sd, dev, precision):
+    net = ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3,
+                      precision=precision)
+    net.module.load_state_dict(sd)
+    return net
+
+
+# ------------------------------------------------------------------------------------------------------
+# single layers through ap_conv2d_debug
+# ------------------------------------------------------------------------------------------------------
+LAYERS = [  # (Cin, Cout, S, stride, pad_mode, transposed, B)
+    (256, 256, 64, 1, "reflect", False, 2),   # ResnetBlock convs
+    (288, 256, 64, 1, "reflect", False, 1),   # ResnetBlock2 first conv (K tail of 32 channels)
+    (288, 256, 64, 1, "zeros", False, 1),     # ResnetBlock2 shortcut
+    (768, 256, 64, 1, "zeros", False, 1),     # model_tri_merge
+    (64, 128, 256, 2, "zeros", False, 1),     # model_tri01 / tri21
+    (64, 64, 256, 2, "zeros", False, 1),      # model_tri11
+    (128, 256, 128, 2, "zeros", False, 1),    # model_tri02 / tri12
+    (128, 128, 128, 2, "zeros", False, 1),    # model_tri22
+    (256, 128, 64, 2, "zeros", True, 1),      # model3.0 (ConvTranspose2d)
+    (128, 64, 128, 2, "zeros", True, 2),      # model3.3 (ConvTranspose2d)
+]
+IMPL_TOL = {"fp32_simt": 5e-5, "fp32": 3e-4, "bf16": 3e-2}  # relative to rms(y)
+
+
+@pytest.mark.parametrize("impl", ["fp32_simt", "fp32", "bf16"])
+@pytest.mark.parametrize("layer", LAYERS, ids=lambda l: f"{l[0]}to{l[1]}_s{l[2]}_st{l[3]}_{l[4]}_{'T' if l[5] else 'C'}")
+def test_conv_layer_matches_torch_cpu(layer, impl, dev):
+    Cin, Cout, S, stride, pad_mode, transposed, B = layer
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + S)
+    x = torch.randn(B, Cin, S, S, generator=g)
+    w = torch.randn((Cin, Cout, 3, 3) if transposed else (Cout, Cin, 3, 3), generator=g) * 0.05
+    if transposed:
+        ref = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+    elif pad_mode == "reflect":
+        ref = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, stride=stride)
+    else:
+        ref = F.conv2d(x, w, stride=stride, padding=1)
+    y, st = ap.conv2d_debug(x.to(dev), w.to(dev), stride=stride, pad=1, pad_mode=pad_mode, transposed=transposed, impl=impl)
+    y = y.cpu()
+    rms = ref.pow(2).mean().sqrt().item()
+    err = (y - ref).abs().max().item()
+    assert err <= IMPL_TOL[impl] * rms, f"max err {err:.3e} vs rms {rms:.3e}"
+    # InstanceNorm statistics emitted by the conv epilogue
+    st = st.cpu()
+    n = ref.shape[2] * ref.shape[3]
+    s_ref = ref.double().sum((2, 3))
+    q_ref = ref.double().pow(2).sum((2, 3))
+    tol = IMPL_TOL[impl] * rms * n
+    assert (st[..., 0] - s_ref).abs().max().item() <= max(tol, 1e-2)
+    assert ((st[..., 1] - q_ref).abs() / q_ref).max().item() <= max(10 * IMPL_TOL[impl], 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------
+# the whole generator
+# ------------------------------------------------------------------------------------------------------
+def _run_case(name, dev, precision, with_taps=False):
+    onc, B, wseed, bstd, iseed, kind = CASES[name]
+    sd = O.make_state_dict(onc, seed=wseed, bias_std=bstd)
+    inputs = O.make_inputs(B, seed=iseed, kind=kind)
+    net = _net(onc, sd, dev, precision)
+    with torch.no_grad():
+        y = net(*[t.to(dev) for t in inputs])
+    torch.cuda.synchronize()
+    return net, sd, inputs, y.cpu()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+def test_forward_matches_golden_fp32(name, precision, dev, golden_dir):
+    net, sd, inputs, y = _run_case(name, dev, precision)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["y"]
+    err = np.abs(y.numpy() - g).max()
+    assert y.shape == g.shape
+    assert err <= FP32_TOL, f"{name} [{precision}]: max-abs {err:.3e} > {FP32_TOL}"
+    assert net.module.last_launch_count() > 40  # the CUDA path ran (no fallback exists)
+
+
+@pytest.mark.parametrize("name", ["c1_line_smooth", "c5_cartoon_noise"])
+def test_forward_bf16_within_stated_tolerance(name, dev, golden_dir):
+    net, sd, inputs, y = _run_case(name, dev, "bf16")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["y"]
+    d = np.abs(y.numpy() - g)
+    assert d.max() <= BF16_MAX and d.mean() <= BF16_MEAN, (d.max(), d.mean())
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+def test_every_intermediate_matches_the_oracle(precision, dev):
+    name = "c1_line_bias"
+    net, sd, inputs, y = _run_case(name, dev, precision)
+    taps = {}
+    y_ref = O.netg_forward(sd, *inputs, tap=lambda n, v: taps.__setitem__(n, v))
+    report = {}
+    for k, ref in taps.items():
+        if k == "pre_tanh":
+            continue
+        got = net.module.debug_read(k).cpu()
+        assert got.shape == ref.shape, k
+        report[k] = (got - ref).abs().max().item()
+    report["out"] = (y - y_ref).abs().max().item()
+    bad = {k: v for k, v in report.items() if v > (1e-3 if k == "out" else 5e-3)}
+    assert not bad, f"taps off: {bad}; all: {report}"
+
+
+def test_host_buffer_entry_point_and_batch_independence(dev):
+    onc, B = 1, 5  # ragged batch, not a power of two
+    sd = O.make_state_dict(onc, seed=21, bias_std=0.1)
+    inputs = O.make_inputs(B, seed=2024, kind="smooth")
+    net = _net(onc, sd, dev, "fp32").module
+    pinned = [t.pin_memory() for t in inputs]
+    y_host = net.forward_host(*pinned)
+    assert not y_host.is_cuda and y_host.shape == (B, onc, 256, 256)
+    with torch.no_grad():
+        y_dev = net(*[t.to(dev) for t in inputs]).cpu()
+        y_one = torch.cat([net(*[t[i:i + 1].to(dev) for t in inputs]).cpu() for i in range(B)])
+    assert (y_host - y_dev).abs().max().item() <= 1e-5   # same kernels, same inputs
+    assert (y_one - y_dev).abs().max().item() <= 1e-4    # frames are independent (InstanceNorm is per sample)
+    y_ref = O.netg_forward(sd, *[t[3:4] for t in inputs])
+    assert (y_dev[3:4] - y_ref).abs().max().item() <= FP32_TOL
+
+
+def test_full_size_batch16_properties(dev):
+    """BASELINE.json config[1] size: B=16.  Oracle on 16 frames is too slow for a unit test, so check
+    size-independent properties: determinism, batch independence against B=1 calls checked by the oracle."""
+    onc, B = 1, 16
+    sd = O.make_state_dict(onc, seed=0)
+    inputs = [t.to(dev) for t in O.make_inputs(B, seed=1016, kind="smooth")]
+    net = _net(onc, sd, dev, "fp32").module
+    with torch.no_grad():
+        y1 = net(*inputs)
+        y2 = net(*inputs)
+        y_last = net(*[t[15:16] for t in inputs])
+    assert torch.isfinite(y1).all() and y1.abs().max().item() <= 1.0
+    assert (y1 - y2).abs().max().item() <= 1e-5
+    assert (y1[15:16] - y_last).abs().max().item() <= 1e-4
+    y_ref = O.netg_forward(sd, *[t[15:16].cpu() for t in inputs])
+    assert (y_last.cpu() - y_ref).abs().max().item() <= FP32_TOL
+
+
+def test_weights_can_be_swapped_and_errors_surface(dev):
+    sd_a, sd_b = O.make_state_dict(1, seed=1), O.make_state_dict(1, seed=2)
+    inputs = [t.to(dev) for t in O.make_inputs(1, seed=5, kind="smooth")]
+    net = _net(1, sd_a, dev, "fp32").module
+    with torch.no_grad():
+        ya = net(*inputs).clone()
+        net.load_state_dict(sd_b)
+        yb = net(*inputs).clone()
+        net.load_state_dict(sd_a)
+        ya2 = net(*inputs)
+    assert (ya - yb).abs().max().item() > 1e-2
+    assert (ya - ya2).abs().max().item() <= 1e-5
+    with torch.no_grad(), pytest.raises(RuntimeError, match="shape"):
+        net(inputs[0], inputs[1], inputs[2], inputs[3][:, :128], inputs[4], inputs[5])
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net(*inputs)  # grad mode on, parameters require grad
+
+
+def test_native_library_is_the_loaded_code_path(dev):
+    maps = open("/proc/self/maps").read()
+    assert "libapnetg.so" in maps
