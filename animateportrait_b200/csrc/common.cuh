@@ -158,6 +158,11 @@ void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
 int umma_init();  // resolves cuTensorMapEncodeTiled, sets func attributes
 
+// ---- tcgen05 fused 7x7 stems (conv_stem.cu) ----
+size_t stem_umma_weight_bytes();
+int launch_pack_stem_umma(const float* src, int cout_s, int coff, uint8_t* img, cudaStream_t st);
+int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* stats, int B, int nprod, cudaStream_t st);
+
 ConvTaps make_taps_conv(int k, int pad, int extra_origin);
 ConvTaps make_taps_convT_phase(int py, int px);
 

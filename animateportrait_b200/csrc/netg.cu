@@ -109,7 +109,8 @@ struct ap_netg {
   size_t ev_used = 0;
   bool loaded = false;
   std::map<std::string, LayerW> w;
-  float* w_stem = nullptr;   // fused stems [49][3][160]
+  float* w_stem = nullptr;   // fused stems [49][3][160] (CUDA-core path)
+  uint8_t* w_stem_img = nullptr;  // fused stems, pre-swizzled bf16 hi/lo smem image (tcgen05 path)
   float* w_out = nullptr;    // [onc][49][64]
   float* b_merge = nullptr;  // [256]
   float* b_out = nullptr;    // [onc]
@@ -294,7 +295,12 @@ int Runner::run(const Inputs& in) {
 
   // ---- three 7x7 stems fused into one Cout=160 problem on the photo (networks.py:1218-1243) ----
   Raw stem = raw(B, 256, 256, 160, true);
-  AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
+  if (prec == AP_PREC_FP32_SIMT) {
+    AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
+  } else if (ph == PH_EXEC) {
+    AP_TRY(launch_stem_umma(in.input, h->w_stem_img, stem.p, stem.stats, B, prec == AP_PREC_FP32X3 ? 3 : 1, st));
+    AP_TRY(mark(CL_STEM, 2.0 * B * 65536.0 * 147 * 160));
+  }
   tap_raw("tri00", stem, 0, 32, 1);
   tap_raw("tri10", stem, 32, 64, 1);
   tap_raw("tri20", stem, 96, 64, 1);
@@ -476,6 +482,7 @@ static void free_weights(ap_netg* h) {
   h->owned.clear();
   h->w.clear();
   h->w_stem = h->w_out = h->b_merge = h->b_out = nullptr;
+  h->w_stem_img = nullptr;
   h->loaded = false;
 }
 
@@ -527,6 +534,7 @@ int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const floa
   };
   int rc = AP_OK;
   AP_TRY(dalloc((size_t)49 * 3 * 160 * 4, (void**)&h->w_stem));
+  if (h->prec != AP_PREC_FP32_SIMT) AP_TRY(dalloc(stem_umma_weight_bytes(), (void**)&h->w_stem_img));
   AP_TRY(dalloc((size_t)h->onc * 49 * 64 * 4, (void**)&h->w_out));
   AP_TRY(dalloc(256 * 4, (void**)&h->b_merge));
   AP_TRY(dalloc(h->onc * 4, (void**)&h->b_out));
@@ -535,9 +543,11 @@ int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const floa
     const float* src = nullptr;
     rc = dev_src(ptrs[idx[s.name + ".weight"]], elems, &src);
     if (rc != AP_OK) break;
-    if (s.name == "model_tri00.1") rc = launch_pack_weights(src, 32, 3, 7, 0, h->w_stem, 160, 0, nullptr, nullptr, st);
-    else if (s.name == "model_tri10.1") rc = launch_pack_weights(src, 64, 3, 7, 0, h->w_stem, 160, 32, nullptr, nullptr, st);
-    else if (s.name == "model_tri20.1") rc = launch_pack_weights(src, 64, 3, 7, 0, h->w_stem, 160, 96, nullptr, nullptr, st);
+    const int stem_off = s.name == "model_tri00.1" ? 0 : (s.name == "model_tri10.1" ? 32 : (s.name == "model_tri20.1" ? 96 : -1));
+    if (stem_off >= 0) {
+      rc = launch_pack_weights(src, s.cout, 3, 7, 0, h->w_stem, 160, stem_off, nullptr, nullptr, st);
+      if (rc == AP_OK && h->w_stem_img) rc = launch_pack_stem_umma(src, s.cout, stem_off, h->w_stem_img, st);
+    }
     else if (s.name == "model3.7") rc = launch_pack_out_weights(src, h->onc, h->w_out, st);
     else {
       LayerW lw;
