@@ -157,11 +157,19 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
 void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
 int umma_init();  // resolves cuTensorMapEncodeTiled, sets func attributes
+int umma_num_sms();
+int tmap_encode(CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box, const uint32_t* estr);
+int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C, int os, int py, int px);
 
 // ---- tcgen05 fused 7x7 stems (conv_stem.cu) ----
 size_t stem_umma_weight_bytes();
 int launch_pack_stem_umma(const float* src, int cout_s, int coff, uint8_t* img, cudaStream_t st);
 int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* stats, int B, int nprod, cudaStream_t st);
+
+// ---- landmark branch (landmark.cu): three direct convs over both landmark maps ----
+int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
+                           const Raw& r0, const Raw& r1, const Raw& r2, int B, cudaStream_t st);
 
 ConvTaps make_taps_conv(int k, int pad, int extra_origin);
 ConvTaps make_taps_convT_phase(int py, int px);

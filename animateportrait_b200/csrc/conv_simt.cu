@@ -183,15 +183,19 @@ int launch_conv_simt(const SimtConvP& p, cudaStream_t st) {
 }
 
 // --------------------------------------------------------------------------------------------
-// Output stage: IN+ReLU (on the fly) -> RefPad3 -> Conv7x7 64->onc -> +bias -> tanh -> NCHW.
-// CTA = 16x16 output pixels; the 22x22 input patch is staged 16 channels at a time.
+// Output stage: IN+ReLU (on the fly) -> RefPad3 -> Conv7x7 64->onc -> +bias -> tanh -> NCHW
+// (networks.py:1277-1279).  0.41 GFLOP per frame against 17 MB of input: HBM-bound, N = onc is far too
+// thin for tensor cores.  CTA = 32x32 output pixels, 128 threads; each thread owns one column of
+// 8 output rows so that a 14-row input column and the 7 ky weights are loaded once per (kx, channel
+// quad) and reused for 8 x 7 x 4 FMAs.  The 38x38 input patch is staged 8 channels at a time with the
+// preceding InstanceNorm + ReLU applied; pixel stride 12 floats keeps the float4 reads conflict-free.
 // --------------------------------------------------------------------------------------------
-constexpr int OC_T = 16, OC_P = OC_T + 6, OC_CS = 20;  // pixel stride 20 floats: conflict-free float4 reads
+constexpr int OC_T = 32, OC_P = OC_T + 6, OC_CG = 8, OC_CS = 12, OC_ROWS = 8;
 
 template <int ONC>
-__global__ void __launch_bounds__(256) out_conv_kernel(const OutConvP p) {
+__global__ void __launch_bounds__(128) out_conv_kernel(const OutConvP p) {
   extern __shared__ __align__(16) float sm[];
-  float* tile = sm;                           // [22*22][20]
+  float* tile = sm;                           // [38*38][12]
   float* wsm = tile + OC_P * OC_P * OC_CS;    // [ONC][49][64]
   float* mean = wsm + ONC * 49 * 64;          // [64]
   float* rstd = mean + 64;                    // [64]
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(256) out_conv_kernel(const OutConvP p) {
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * OC_T, x0 = blockIdx.x * OC_T;
   const int S = 256;
-  for (int i = tid; i < ONC * 49 * 64; i += 256) wsm[i] = p.w[i];
+  for (int i = tid; i < ONC * 49 * 64; i += 128) wsm[i] = p.w[i];
   if (tid < 64) {
     const double inv = 1.0 / (double)(S * S);
     const double su = p.stats[((size_t)n * 64 + tid) * 2 + 0];
@@ -210,19 +214,20 @@ __global__ void __launch_bounds__(256) out_conv_kernel(const OutConvP p) {
     mean[tid] = (float)m;
     rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
   }
-  __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
-  float acc[ONC];
+  const int tx = tid & 31, tg = tid >> 5;
+  float acc[ONC][OC_ROWS];
 #pragma unroll
-  for (int o = 0; o < ONC; ++o) acc[o] = 0.f;
+  for (int o = 0; o < ONC; ++o)
+#pragma unroll
+    for (int r = 0; r < OC_ROWS; ++r) acc[o][r] = 0.f;
 
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    // stage 22x22 pixels x 16 channels (float4 per thread-iteration)
-    for (int i = tid; i < OC_P * OC_P * 4; i += 256) {
-      const int pp = i >> 2, cq = (i & 3) * 4;
+  for (int c0 = 0; c0 < 64; c0 += OC_CG) {
+    __syncthreads();  // previous group fully consumed (and, first time, mean/rstd/weights visible)
+    for (int i = tid; i < OC_P * OC_P * 2; i += 128) {
+      const int pp = i >> 1, cq = (i & 1) * 4;
       const int py = pp / OC_P, px = pp - py * OC_P;
       const int iy = reflect_idx(y0 + py - 3, S), ix = reflect_idx(x0 + px - 3, S);
-      float4 v = *reinterpret_cast<const float4*>(p.raw + ((size_t)(n * S + iy) * S + ix) * 64 + c0 + cq);
+      float4 v = __ldg(reinterpret_cast<const float4*>(p.raw + ((size_t)(n * S + iy) * S + ix) * 64 + c0 + cq));
       v.x = fmaxf((v.x - mean[c0 + cq + 0]) * rstd[c0 + cq + 0], 0.f);
       v.y = fmaxf((v.y - mean[c0 + cq + 1]) * rstd[c0 + cq + 1], 0.f);
       v.z = fmaxf((v.z - mean[c0 + cq + 2]) * rstd[c0 + cq + 2], 0.f);
@@ -231,30 +236,35 @@ __global__ void __launch_bounds__(256) out_conv_kernel(const OutConvP p) {
     }
     __syncthreads();
 #pragma unroll 1
-    for (int ky = 0; ky < 7; ++ky) {
+    for (int kx = 0; kx < 7; ++kx) {
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float* ip = tile + ((ty + ky) * OC_P + tx + kx) * OC_CS;
-        const float* wp = wsm + (ky * 7 + kx) * 64 + c0;
+      for (int cq = 0; cq < OC_CG; cq += 4) {
+        float4 a[OC_ROWS + 6];
+        const float* ip = tile + ((tg * OC_ROWS) * OC_P + tx + kx) * OC_CS + cq;
 #pragma unroll
-        for (int cq = 0; cq < 16; cq += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(ip + cq);
+        for (int r = 0; r < OC_ROWS + 6; ++r) a[r] = *reinterpret_cast<const float4*>(ip + r * OC_P * OC_CS);
 #pragma unroll
-          for (int o = 0; o < ONC; ++o) {
-            const float4 w = *reinterpret_cast<const float4*>(wp + o * 49 * 64 + cq);
-            acc[o] = fmaf(a.x, w.x, acc[o]);
-            acc[o] = fmaf(a.y, w.y, acc[o]);
-            acc[o] = fmaf(a.z, w.z, acc[o]);
-            acc[o] = fmaf(a.w, w.w, acc[o]);
+        for (int o = 0; o < ONC; ++o) {
+#pragma unroll
+          for (int ky = 0; ky < 7; ++ky) {
+            const float4 w = *reinterpret_cast<const float4*>(wsm + (o * 49 + ky * 7 + kx) * 64 + c0 + cq);
+#pragma unroll
+            for (int r = 0; r < OC_ROWS; ++r) {
+              acc[o][r] = fmaf(a[r + ky].x, w.x, acc[o][r]);
+              acc[o][r] = fmaf(a[r + ky].y, w.y, acc[o][r]);
+              acc[o][r] = fmaf(a[r + ky].z, w.z, acc[o][r]);
+              acc[o][r] = fmaf(a[r + ky].w, w.w, acc[o][r]);
+            }
           }
         }
       }
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int o = 0; o < ONC; ++o)
-    p.out[((size_t)(n * ONC + o) * S + y0 + ty) * S + x0 + tx] = tanhf(acc[o] + p.bias[o]);
+#pragma unroll
+    for (int r = 0; r < OC_ROWS; ++r)
+      p.out[((size_t)(n * ONC + o) * S + y0 + tg * OC_ROWS + r) * S + x0 + tx] = tanhf(acc[o][r] + p.bias[o]);
 }
 
 int launch_out_conv(const OutConvP& p, cudaStream_t st) {
@@ -262,10 +272,10 @@ int launch_out_conv(const OutConvP& p, cudaStream_t st) {
   const size_t smem = (size_t)(OC_P * OC_P * OC_CS + p.onc * 49 * 64 + 128) * sizeof(float);
   if (p.onc == 1) {
     AP_CUDA(cudaFuncSetAttribute(out_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    out_conv_kernel<1><<<grid, 256, smem, st>>>(p);
+    out_conv_kernel<1><<<grid, 128, smem, st>>>(p);
   } else if (p.onc == 3) {
     AP_CUDA(cudaFuncSetAttribute(out_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    out_conv_kernel<3><<<grid, 256, smem, st>>>(p);
+    out_conv_kernel<3><<<grid, 128, smem, st>>>(p);
   } else {
     set_error("out_conv: output_nc=%d unsupported", p.onc);
     return AP_ERR_UNSUPPORTED;

@@ -36,9 +36,12 @@ constexpr int ST_ASLOT = 2 * ST_APLANE;          // hi + lo
 constexpr int ST_PW = 70, ST_PH = 8;             // patch: 64+6 columns, 2+6 rows
 constexpr int ST_PATCH = 3 * ST_PH * ST_PW;      // words
 constexpr int ST_THREADS = 288;
-constexpr size_t ST_SMEM = 1024 + ST_WBYTES + 3 * ST_ASLOT + ST_PATCH * 4 + 256;
+constexpr int ST_EPI = 4 * 2 * 4096;             // two 4 KB staging slabs per epilogue warp
+constexpr int ST_RING = 2 * ST_ASLOT;            // two A slots: chunk c lives in slot c & 1
+constexpr size_t ST_SMEM = 1024 + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4 + 256;
 
 struct StemP {
+  CUtensorMap tmO;       // fp32 NHWC output [B,256,256,160], box {32 ch, 32 px, 1 row, 1 image}
   const float* in;       // [B,3,256,256] NCHW fp32
   const uint8_t* wimg;   // ST_WBYTES: [plane][chunk][160 rows][64 k] bf16, 128B-swizzled smem image
   float* out;            // raw NHWC [B,256,256,160]
@@ -82,18 +85,20 @@ __device__ __forceinline__ void stem_build_chunk(const uint32_t* __restrict__ pb
 }
 
 template <int NPROD>
-__global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const StemP p) {
+__global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_constant__ StemP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // layout: W | A ring | patch | barriers
+  // layout: W | A ring (2 slots) | epilogue slabs | patch | barriers
   const uint32_t sW = smem_base;
   const uint32_t sA = smem_base + ST_WBYTES;
   uint8_t* gA = sgen + ST_WBYTES;
-  uint32_t* patch = reinterpret_cast<uint32_t*>(sgen + ST_WBYTES + 3 * ST_ASLOT);
-  const uint32_t bars = smem_base + ST_WBYTES + 3 * ST_ASLOT + ST_PATCH * 4;
+  const uint32_t epi_s = smem_base + ST_WBYTES + ST_RING;
+  uint8_t* epi_gen = sgen + ST_WBYTES + ST_RING;
+  uint32_t* patch = reinterpret_cast<uint32_t*>(sgen + ST_WBYTES + ST_RING + ST_EPI);
+  const uint32_t bars = smem_base + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4;
   // full[c] +0..16, empty[c] +24..40, tfull[a] +48,56, tempty[a] +64,72, wbar +80, tmem ptr +96
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sgen + ST_WBYTES + 3 * ST_ASLOT + ST_PATCH * 4 + 96);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sgen + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4 + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous tile range of this CTA
@@ -104,6 +109,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const StemP p)
 
   if (warp == 0) {
     if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO) : "memory");
       for (int c = 0; c < 3; ++c) {
         mbar_init(bars + 8 * c, 128);      // full: every builder thread arrives
         mbar_init(bars + 24 + 8 * c, 1);   // empty: one tcgen05.commit
@@ -145,8 +151,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const StemP p)
         for (int c = 0; c < 3; ++c) {
           mbar_wait(bars + 8 * c, (uint32_t)it & 1u);
           tc_fence_after();
-          const uint64_t a_hi = make_sw128_desc(sA + c * ST_ASLOT);
-          const uint64_t a_lo = make_sw128_desc(sA + c * ST_ASLOT + ST_APLANE);
+          const uint64_t a_hi = make_sw128_desc(sA + (c & 1) * ST_ASLOT);
+          const uint64_t a_lo = make_sw128_desc(sA + (c & 1) * ST_ASLOT + ST_APLANE);
           const uint64_t w_hi = make_sw128_desc(sW + c * ST_WCHUNK);
           const uint64_t w_lo = make_sw128_desc(sW + (3 + c) * ST_WCHUNK);
           const int ksteps = (c == 2) ? 2 : 4;
@@ -187,25 +193,30 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const StemP p)
         patch[idx] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // chunk c is built in slot c & 1: chunk 0 reuses the slot of the previous tile's chunk 2,
+      // chunk 1 the slot of the previous tile's chunk 1, chunk 2 the slot of this tile's chunk 0
       const uint32_t par = ((uint32_t)it & 1u) ^ 1u;
-      mbar_wait(bars + 24 + 0, par);
-      stem_build_chunk<0>(pbase, gA + 0 * ST_ASLOT, r8, atom_off);
+      mbar_wait(bars + 24 + 16, par);
+      stem_build_chunk<0>(pbase, gA, r8, atom_off);
       fence_proxy_async();
       mbar_arrive(bars + 0);
       mbar_wait(bars + 24 + 8, par);
-      stem_build_chunk<1>(pbase, gA + 1 * ST_ASLOT, r8, atom_off);
+      stem_build_chunk<1>(pbase, gA + ST_ASLOT, r8, atom_off);
       fence_proxy_async();
       mbar_arrive(bars + 8);
-      mbar_wait(bars + 24 + 16, par);
-      stem_build_chunk<2>(pbase, gA + 2 * ST_ASLOT, r8, atom_off);
+      mbar_wait(bars + 24 + 0, (uint32_t)it & 1u);
+      stem_build_chunk<2>(pbase, gA, r8, atom_off);
       fence_proxy_async();
       mbar_arrive(bars + 16);
     }
   } else {
     // ===================== epilogue (warps 5..8) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int yy = row >> 6, xx = row & 63;
+    const int row0 = q * 32;
+    const int yy = row0 >> 6, xx0 = row0 & 63;
+    uint8_t* slab_gen = epi_gen + q * 8192;
+    const uint32_t slab_s = epi_s + q * 8192;
+    uint32_t blk = 0;
     float ssum[5], ssq[5];
 #pragma unroll
     for (int g = 0; g < 5; ++g) { ssum[g] = 0.f; ssq[g] = 0.f; }
@@ -216,14 +227,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const StemP p)
       const int acc = it & 1;
       mbar_wait(bars + 48 + 8 * acc, ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
-      float* orow = p.out + ((size_t)(img * 256 + y0 + yy) * 256 + x0 + xx) * ST_N;
 #pragma unroll
-      for (int g = 0; g < 5; ++g) {
+      for (int g = 0; g < 5; ++g, ++blk) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + g * 32), v);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(orow + g * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + (uint32_t)(acc * 256 + g * 32), v);
+        const uint32_t sl = (blk & 1u) * 4096;
+        epi_store_block<1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, g * 32, x0 + xx0, y0 + yy, img);
         float sq[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const StemP p)
         }
       }
     }
+    if (lane == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -295,7 +305,9 @@ int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* s
     AP_CUDA(cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
     AP_CUDA(cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
   }
-  StemP p{in, wimg, out, stats, B * 512};
+  StemP p{};
+  AP_TRY(tmap_encode_out(&p.tmO, out, B, 256, 256, ST_N, 1, 0, 0));
+  p.in = in; p.wimg = wimg; p.out = out; p.stats = stats; p.tiles = B * 512;
   const int grid = p.tiles < g_stem_sms ? p.tiles : g_stem_sms;
   if (nprod == 3)
     stem_umma_kernel<3><<<grid, ST_THREADS, ST_SMEM, st>>>(p);

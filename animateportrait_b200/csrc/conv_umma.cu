@@ -1,20 +1,26 @@
-// tcgen05 implicit-GEMM convolution for sm_100a.
+// tcgen05 implicit-GEMM convolution for sm_100a: persistent, warp-specialised, TMEM double-buffered.
 //
-// One CTA computes a 128-pixel x BN-channel tile of a tap-list convolution (ConvGeom, common.cuh):
-//   D[128 px, BN] = sum over taps t, channel chunks c0:  A_t[128 px, 64 ch] * W_t[BN, 64 ch]^T
+// One work item = a 128-pixel x bn-channel tile of a tap-list convolution (ConvGeom, common.cuh):
+//   D[128 px, bn] = sum over taps t, channel chunks c0:  A_t[128 px, 64 ch] * W_t[bn, 64 ch]^T
 // * A tiles come straight from the NHWC bf16 activation buffer through a 4-D TMA box
 //   {64 ch, TW px, TH rows, 1 image} placed at (c0, x0*stride + dx_t, y0*stride + dy_t, n): no im2col.
 //   Reflection padding = halo ring written by the producer; zero padding = TMA out-of-bounds fill on
 //   the un-haloed view; stride-2 convs use TMA elementStrides = 2; the four phases of
-//   ConvTranspose2d(k3,s2,p1,op1) are tap subsets with a strided output scatter.
-// * W tiles come from tap-major, K-major packed weights [slab][Cout][Cin] through a 3-D TMA box.
+//   ConvTranspose2d(k3,s2,p1,op1) are tap subsets with a strided output view.
+// * W tiles come from tap-major, K-major packed weights [slab][Cout][Cin] through 3-D TMA boxes of 64 rows.
 // * Both land in shared memory in the 128-byte-swizzled K-major layout that tcgen05.mma reads via
 //   shared-memory descriptors; accumulation is fp32 in TMEM.
 // * NPROD = 3 runs A_hi*W_hi + A_hi*W_lo + A_lo*W_hi (bf16 hi/lo split) into the same accumulator:
 //   fp32-accurate results (9.5e-5 end to end); NPROD = 1 is plain bf16.
+// * CTAs are persistent (grid = #SMs, one CTA per SM) and walk a static item list.  Items are full
+//   tiles (bn = Cout) for as many whole waves as the tile count gives; the tiles of the last, partial
+//   wave are split along N into 2 or 4 items so that the tail occupies every SM (512 tiles on 148 SMs:
+//   3 waves of full tiles + 136 half tiles instead of a fourth, 46%-full wave).
+// * Two 256-column TMEM accumulators: the epilogue of item i overlaps the MMAs of item i+1.
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-//   warps 2..5 = epilogue: tcgen05.ld the accumulator, store raw fp32 NHWC, and reduce per-channel
-//   sum / sum-of-squares for the following InstanceNorm with a 31-shuffle butterfly per 32 columns.
+//   warps 2..5 = epilogue: tcgen05.ld 32 columns at a time, stage them in a swizzled 4 KB slab and
+//   TMA-store the {32 ch, 32 px} box (coalesced, asynchronous), and reduce per-channel sum /
+//   sum-of-squares for the following InstanceNorm with a 31-shuffle butterfly per 32 columns.
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -27,35 +33,60 @@ void launches_add(int n);
 struct alignas(64) UmmaParams {
   CUtensorMap tmA[2];  // hi, lo
   CUtensorMap tmW[2];
+  CUtensorMap tmO;     // fp32 output view (phase-strided for transposed convs)
   int ntaps;
   int8_t dy[9], dx[9];
   uint8_t slab[9];
   int kchunks, last_ksteps, cin_off;
   int tiles_x, tiles_y, TW, TH, stride;
-  float* out;
-  int os, py, px, Hout, Wout, out_C, out_coff;
+  int out_coff;
   double* stats;
   int stat_C, stat_coff;
+  int n_full, split, n_items;  // item list: n_full full tiles, then (tiles - n_full) * split N-parts
 };
 
 struct UmmaConv {
   UmmaParams p;
-  int BN, nprod, stages;
+  int BN, nprod;
   dim3 grid;
   size_t smem;
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+constexpr int EPI_SLABS = 2;             // staging slabs per epilogue warp
+constexpr int EPI_BYTES = 4 * EPI_SLABS * 4096;
 
 template <int BN, int NPROD>
 struct UmmaCfg {
   static constexpr int W_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (226 * 1024 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int EXTRA_BYTES = 256 + 2 * BN * 4;  // barriers + tmem ptr, stat partials
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EXTRA_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
+
+struct Item {
+  int img, ty, tx, n0, bn;
+};
+
+__device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int BN) {
+  int m, n0 = 0, bn = BN;
+  if (item < p.n_full) {
+    m = item;
+  } else {
+    const int r = item - p.n_full;
+    m = p.n_full + r / p.split;
+    bn = BN / p.split;
+    n0 = (r % p.split) * bn;
+  }
+  Item it;
+  it.tx = m % p.tiles_x; m /= p.tiles_x;
+  it.ty = m % p.tiles_y; m /= p.tiles_y;
+  it.img = m;
+  it.n0 = n0;
+  it.bn = bn;
+  return it;
+}
 
 template <int BN, int NPROD>
 __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
@@ -64,25 +95,19 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barrier layout: full[s] at bars + 8*s, empty[s] at bars + 64 + 8*s, tmem_full at bars + 128, tmem ptr at +136
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 136);
-  float* s_sum = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 256);
-  float* s_sq = s_sum + BN;
+  const uint32_t epi_s = smem_base + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bars = epi_s + EPI_BYTES;
+  // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; t /= p.tiles_y;
-  const int img = t;
-  const int n0 = blockIdx.y * BN;
   const int iters = p.ntaps * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO) : "memory");
     if (NPROD == 3) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[1]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[1]) : "memory");
@@ -91,125 +116,145 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       mbar_init(bars + 8 * s, 1);
       mbar_init(bars + 64 + 8 * s, 1);
     }
-    mbar_init(bars + 128, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bars + 128 + 8 * a, 1);  // tfull: one tcgen05.commit
+      mbar_init(bars + 144 + 8 * a, 4);  // tempty: one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)BN)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
-    for (int c = threadIdx.x - 64; c < 2 * BN; c += 128) s_sum[c] = 0.f;
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int x0 = tx * p.TW * p.stride, y0 = ty * p.TH * p.stride;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
-        const int tap = it / p.kchunks, chunk = it - tap * p.kchunks;
-        const uint32_t full = bars + 8 * s;
-        mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
-        const int ca = p.cin_off + chunk * 64, cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
-        tma_load_4d(sa, &p.tmA[0], full, ca, cx, cy, img);
-        if (NPROD == 3) {
-          tma_load_4d(sa + A_TILE_BYTES, &p.tmA[1], full, ca, cx, cy, img);
-          tma_load_3d(sa + 2 * A_TILE_BYTES, &p.tmW[0], full, chunk * 64, n0, p.slab[tap]);
-          tma_load_3d(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES, &p.tmW[1], full, chunk * 64, n0, p.slab[tap]);
-        } else {
-          tma_load_3d(sa + A_TILE_BYTES, &p.tmW[0], full, chunk * 64, n0, p.slab[tap]);
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item w = decode_item(p, item, BN);
+        const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
+        const int nbox = w.bn >> 6;
+        const uint32_t tx_bytes = (NPROD == 3 ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + w.bn * 128);
+        for (int it = 0; it < iters; ++it, ++cnt) {
+          const uint32_t s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1u;
+          mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
+          const int tap = it / p.kchunks, chunk = it - tap * p.kchunks;
+          const uint32_t full = bars + 8 * s;
+          mbar_expect_tx(full, tx_bytes);
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const int ca = p.cin_off + chunk * 64, cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
+          tma_load_4d(sa, &p.tmA[0], full, ca, cx, cy, w.img);
+          if (NPROD == 3) {
+            tma_load_4d(sa + A_TILE_BYTES, &p.tmA[1], full, ca, cx, cy, w.img);
+            for (int b = 0; b < nbox; ++b) {
+              tma_load_3d(sa + 2 * A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
+              tma_load_3d(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES + b * 8192, &p.tmW[1], full, chunk * 64, w.n0 + 64 * b,
+                          p.slab[tap]);
+            }
+          } else {
+            for (int b = 0; b < nbox; ++b)
+              tma_load_3d(sa + A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
-      // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrite), 1 afterwards
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bars + 8 * s, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int chunk = it % p.kchunks;
-        const int ksteps = (chunk == p.kchunks - 1) ? p.last_ksteps : 4;
-        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
-        const uint64_t a_hi = make_sw128_desc(sa);
-        if (NPROD == 3) {
-          const uint64_t a_lo = make_sw128_desc(sa + A_TILE_BYTES);
-          const uint64_t w_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
-          const uint64_t w_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t o = (uint64_t)(k * 2);  // +32 bytes (16 bf16) inside the 128-B swizzle row, >>4
-            umma_bf16(tmem_base, a_hi + o, w_hi + o, idesc, first);
-            first = 1;
-            umma_bf16(tmem_base, a_hi + o, w_lo + o, idesc, 1);
-            umma_bf16(tmem_base, a_lo + o, w_hi + o, idesc, 1);
+      uint32_t cnt = 0, local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+        const Item w = decode_item(p, item, BN);
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+        // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(w.bn >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t acc = local & 1u;
+        mbar_wait(bars + 144 + 8 * acc, ((local >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 256u;
+        uint32_t first = 0;  // 0 for the very first MMA of the item (overwrite), 1 afterwards
+        for (int it = 0; it < iters; ++it, ++cnt) {
+          const uint32_t s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1u;
+          mbar_wait(bars + 8 * s, ph);
+          tc_fence_after();
+          const int chunk = it % p.kchunks;
+          const int ksteps = (chunk == p.kchunks - 1) ? p.last_ksteps : 4;
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = make_sw128_desc(sa);
+          if (NPROD == 3) {
+            const uint64_t a_lo = make_sw128_desc(sa + A_TILE_BYTES);
+            const uint64_t w_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
+            const uint64_t w_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);  // +32 bytes (16 bf16) inside the 128-B swizzle row, >>4
+              umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+              first = 1;
+              umma_bf16(d, a_hi + o, w_lo + o, idesc, 1);
+              umma_bf16(d, a_lo + o, w_hi + o, idesc, 1);
+            }
+          } else {
+            const uint64_t w_hi = make_sw128_desc(sa + A_TILE_BYTES);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+              first = 1;
+            }
           }
-        } else {
-          const uint64_t w_hi = make_sw128_desc(sa + A_TILE_BYTES);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t o = (uint64_t)(k * 2);
-            umma_bf16(tmem_base, a_hi + o, w_hi + o, idesc, first);
-            first = 1;
-          }
+          umma_commit(bars + 64 + 8 * s);  // frees the smem stage when these MMAs retire
         }
-        umma_commit(bars + 64 + 8 * s);             // frees the smem stage when these MMAs retire
-        if (it == iters - 1) umma_commit(bars + 128);  // accumulator complete
+        umma_commit(bars + 128 + 8 * acc);  // accumulator complete
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;                   // accumulator row = pixel index inside the tile
-    const int yy = row / p.TW, xx = row - yy * p.TW;
-    const int oy = (ty * p.TH + yy) * p.os + p.py, ox = (tx * p.TW + xx) * p.os + p.px;
-    float* orow = p.out + ((size_t)(img * p.Hout + oy) * p.Wout + ox) * p.out_C + p.out_coff + n0;
-    mbar_wait(bars + 128, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row0 = q * 32;
+    const int yy = row0 / p.TW, xx0 = row0 - yy * p.TW;
+    uint8_t* slab_gen = epi_gen + q * (EPI_SLABS * 4096);
+    const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
+    uint32_t local = 0, blk = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      const Item w = decode_item(p, item, BN);
+      const uint32_t acc = local & 1u;
+      mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
+      tc_fence_after();
+      const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
+      double* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + w.n0 + lane) * 2 : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
+        const uint32_t sl = (blk % EPI_SLABS) * 4096;
+        epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
+        if (strow != nullptr) {
+          float sq[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      if (p.stats != nullptr) {
-        float sq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-        const float cs = butterfly_colsum(v, lane);
-        const float cq = butterfly_colsum(sq, lane);
-        atomicAdd(&s_sum[c0 + lane], cs);
-        atomicAdd(&s_sq[c0 + lane], cq);
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float cs = butterfly_colsum(v, lane);
+          const float cq = butterfly_colsum(sq, lane);
+          atomicAdd(strow + (size_t)c0 * 2, (double)cs);
+          atomicAdd(strow + (size_t)c0 * 2 + 1, (double)cq);
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < BN; c += 128) {
-        double* st = p.stats + ((size_t)img * p.stat_C + p.stat_coff + n0 + c) * 2;
-        atomicAdd(st, (double)s_sum[c]);
-        atomicAdd(st + 1, (double)s_sq[c]);
-      }
-    }
+    if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -217,6 +262,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
 // host side
 // ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int g_sms = 0;
 
 template <int BN, int NPROD>
 static int set_attr() {
@@ -232,6 +278,9 @@ int umma_init() {
   AP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   AP_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, AP_ERR_CUDA,
              "cuTensorMapEncodeTiled not available from the driver");
+  int dev = 0;
+  AP_CUDA(cudaGetDevice(&dev));
+  AP_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   AP_TRY((set_attr<64, 1>()));
   AP_TRY((set_attr<128, 1>()));
   AP_TRY((set_attr<256, 1>()));
@@ -242,13 +291,32 @@ int umma_init() {
   return AP_OK;
 }
 
-static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, const cuuint32_t* estr) {
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+int umma_num_sms() { return g_sms; }
+
+// dtype: 0 = bf16, 1 = fp32.  All maps use SWIZZLE_128B (inner box = 128 bytes).
+int tmap_encode(CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box, const uint32_t* estr) {
+  AP_TRY(umma_init());
+  cuuint64_t d[5], s[5];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+  CUresult r = g_encode(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                        const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  AP_REQUIRE(r == CUDA_SUCCESS, AP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  AP_REQUIRE(r == CUDA_SUCCESS, AP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dtype %d)", (int)r, rank,
+             dtype);
   return AP_OK;
+}
+
+// fp32 NHWC output view for the epilogue's TMA stores: box {32 ch, 32 px, 1 row, 1 image}; `os` > 1 selects
+// the (py, px) phase of a transposed conv as a strided view.
+int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C, int os, int py, int px) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)(Wout / os), (uint64_t)(Hout / os), (uint64_t)B};
+  const uint64_t str[3] = {(uint64_t)os * C * 4, (uint64_t)os * Wout * C * 4, (uint64_t)Hout * Wout * C * 4};
+  const uint32_t box[4] = {32, 32, 1, 1};
+  const uint32_t es[4] = {1, 1, 1, 1};
+  return tmap_encode(m, 1, out + ((size_t)py * Wout + px) * C, 4, dims, str, box, es);
 }
 
 // `in` must be a bf16 activation. Zero-padded convs address the un-haloed interior (TMA fills
@@ -279,24 +347,25 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   const bool padded_view = g.reflect != 0;
   const int Hp = in.H + 2 * in.pad, Wp = in.W + 2 * in.pad;
   const int org = padded_view ? in.pad : 0;
-  const cuuint64_t adims[4] = {(cuuint64_t)in.C, (cuuint64_t)(padded_view ? Wp : in.W),
-                               (cuuint64_t)(padded_view ? Hp : in.H), (cuuint64_t)in.B};
-  const cuuint64_t astr[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)Wp * in.C * 2, (cuuint64_t)Hp * Wp * in.C * 2};
-  const cuuint32_t abox[4] = {64, (cuuint32_t)(TW * g.stride), (cuuint32_t)(TH * g.stride), 1};
-  const cuuint32_t aes[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  const uint64_t adims[4] = {(uint64_t)in.C, (uint64_t)(padded_view ? Wp : in.W), (uint64_t)(padded_view ? Hp : in.H),
+                             (uint64_t)in.B};
+  const uint64_t astr[3] = {(uint64_t)in.C * 2, (uint64_t)Wp * in.C * 2, (uint64_t)Hp * Wp * in.C * 2};
+  const uint32_t abox[4] = {64, (uint32_t)(TW * g.stride), (uint32_t)(TH * g.stride), 1};
+  const uint32_t aes[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
   const size_t view_off = padded_view ? 0 : ((size_t)in.pad * Wp + in.pad) * in.C;
-  int rc = encode(&p.tmA[0], reinterpret_cast<const __nv_bfloat16*>(in.p0) + view_off, 4, adims, astr, abox, aes);
+  int rc = tmap_encode(&p.tmA[0], 0, reinterpret_cast<const __nv_bfloat16*>(in.p0) + view_off, 4, adims, astr, abox, aes);
   if (rc == AP_OK && nprod == 3)
-    rc = encode(&p.tmA[1], reinterpret_cast<const __nv_bfloat16*>(in.p1) + view_off, 4, adims, astr, abox, aes);
-  // weight maps [slab][Cout][Cin]
+    rc = tmap_encode(&p.tmA[1], 0, reinterpret_cast<const __nv_bfloat16*>(in.p1) + view_off, 4, adims, astr, abox, aes);
+  // weight maps [slab][Cout][Cin], boxes of 64 output channels
   for (int i = 0; i < g.taps.n; ++i)
     AP_REQUIRE(g.taps.slab[i] < 9, AP_ERR_INVALID, "umma conv: only 3x3 weight slabs are packed for tcgen05");
-  const cuuint64_t wdims[3] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Cout, 9};
-  const cuuint64_t wstr[2] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Cin * g.Cout * 2};
-  const cuuint32_t wbox[3] = {64, (cuuint32_t)c->BN, 1};
-  const cuuint32_t wes[3] = {1, 1, 1};
-  if (rc == AP_OK) rc = encode(&p.tmW[0], w_hi, 3, wdims, wstr, wbox, wes);
-  if (rc == AP_OK && nprod == 3) rc = encode(&p.tmW[1], w_lo, 3, wdims, wstr, wbox, wes);
+  const uint64_t wdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
+  const uint64_t wstr[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * g.Cout * 2};
+  const uint32_t wbox[3] = {64, 64, 1};
+  const uint32_t wes[3] = {1, 1, 1};
+  if (rc == AP_OK) rc = tmap_encode(&p.tmW[0], 0, w_hi, 3, wdims, wstr, wbox, wes);
+  if (rc == AP_OK && nprod == 3) rc = tmap_encode(&p.tmW[1], 0, w_lo, 3, wdims, wstr, wbox, wes);
+  if (rc == AP_OK) rc = tmap_encode_out(&p.tmO, out_raw, g.B, g.Hout, g.Wout, out_C, g.os, g.py, g.px);
   if (rc != AP_OK) { delete c; return rc; }
 
   p.ntaps = g.taps.n;
@@ -312,11 +381,20 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   p.TW = TW; p.TH = TH;
   p.tiles_x = g.Wv / TW; p.tiles_y = g.Hv / TH;
   p.stride = g.stride;
-  p.out = out_raw;
-  p.os = g.os; p.py = g.py; p.px = g.px; p.Hout = g.Hout; p.Wout = g.Wout;
-  p.out_C = out_C; p.out_coff = out_coff;
+  p.out_coff = out_coff;
   p.stats = stats; p.stat_C = stat_C; p.stat_coff = stat_coff;
-  c->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * g.B), (unsigned)(g.Cout / c->BN));
+  // item list: whole waves of full tiles, the remainder split along N so the tail fills the machine
+  const int tiles = p.tiles_x * p.tiles_y * g.B;
+  const int G = g_sms > 0 ? g_sms : 148;
+  const int rem = tiles % G;
+  int split = 1;
+  if (rem > 0) {
+    while (split < 4 && rem * split * 2 <= G && c->BN / (split * 2) >= 64) split *= 2;
+  }
+  p.split = split;
+  p.n_full = tiles - rem;
+  p.n_items = p.n_full + rem * split;
+  c->grid = dim3((unsigned)(p.n_items < G ? p.n_items : G), 1);
   *out = c;
   return AP_OK;
 }

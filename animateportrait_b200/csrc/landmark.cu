@@ -1,0 +1,134 @@
+// Landmark branch `model_landmark_trans` (Module2/models/networks.py:1280-1282), applied to land1 and
+// land2 (networks.py:1331-1332):  Conv3x3 1->8 +IN+ReLU ; Conv3x3 s2 8->16 +IN+ReLU ; Conv3x3 s2 16->16 +IN.
+//
+// 0.13 GFLOP per frame but 13.6 MB of traffic: HBM-bound, far too thin for tensor cores (Cout <= 16).
+// One direct-convolution kernel template, one thread per output pixel holding all COUT accumulators;
+// both landmark maps go through the same launch as a batch of 2B images.  The InstanceNorm + ReLU of
+// the PREVIOUS layer is applied while the taps are loaded (raw conv outputs + per-(n,c) sums are what
+// travels through HBM, each tensor written once and read once); zero padding is applied after the
+// normalisation, as in the reference.  Biases cancel in the affine-less InstanceNorm.
+#include "common.cuh"
+
+namespace ap {
+
+void launches_add(int n);
+
+struct LandP {
+  const float* in0;   // CIN == 1: land1 [B,1,256,256];  else raw NHWC [2B,Hin,Win,CIN]
+  const float* in1;   // CIN == 1: land2
+  const double* in_stats;  // [2B][CIN][2] (CIN > 1)
+  const float* w;     // [9][CIN][COUT] fp32
+  float* out;         // raw NHWC [2B,Hout,Wout,COUT]
+  double* out_stats;  // [2B][COUT][2]
+  int B, Hin, Hout;
+};
+
+template <int CIN, int COUT, int STRIDE>
+__global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
+  __shared__ __align__(16) float sw[9 * CIN * COUT];
+  __shared__ float s_mean[CIN], s_rstd[CIN];
+  __shared__ float s_red[2 * COUT];
+  const int tid = threadIdx.x;
+  const int HWo = p.Hout * p.Hout;
+  const int gpix = blockIdx.x * 256 + tid;  // Hout*Hout is a multiple of 256: one image per CTA
+  const int n = gpix / HWo;
+  const int pix = gpix - n * HWo;
+  const int oy = pix / p.Hout, ox = pix - oy * p.Hout;
+  for (int i = tid; i < 9 * CIN * COUT; i += 256) sw[i] = p.w[i];
+  if (tid < 2 * COUT) s_red[tid] = 0.f;
+  if (CIN > 1 && tid < CIN) {
+    const double inv = 1.0 / (double)(p.Hin * p.Hin);
+    const double su = p.in_stats[((size_t)n * CIN + tid) * 2 + 0];
+    const double sq = p.in_stats[((size_t)n * CIN + tid) * 2 + 1];
+    const double m = su * inv;
+    double var = sq * inv - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = (float)m;
+    s_rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * STRIDE + ky - 1;
+    if (iy < 0 || iy >= p.Hin) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * STRIDE + kx - 1;
+      if (ix < 0 || ix >= p.Hin) continue;
+      const float* wt = sw + (ky * 3 + kx) * CIN * COUT;
+      if (CIN == 1) {
+        const float* src = (n < p.B) ? p.in0 + (size_t)n * p.Hin * p.Hin : p.in1 + (size_t)(n - p.B) * p.Hin * p.Hin;
+        const float v = __ldg(src + iy * p.Hin + ix);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wt[o], acc[o]);
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(p.in0 + ((size_t)(n * p.Hin + iy) * p.Hin + ix) * CIN);
+#pragma unroll
+        for (int c4 = 0; c4 < CIN / 4; ++c4) {
+          const float4 r = __ldg(src + c4);
+          float v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            const float a = fmaxf((v[e] - s_mean[c]) * s_rstd[c], 0.f);  // IN + ReLU of the previous layer
+#pragma unroll
+            for (int o4 = 0; o4 < COUT / 4; ++o4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wt + c * COUT + o4 * 4);
+              acc[o4 * 4 + 0] = fmaf(a, w4.x, acc[o4 * 4 + 0]);
+              acc[o4 * 4 + 1] = fmaf(a, w4.y, acc[o4 * 4 + 1]);
+              acc[o4 * 4 + 2] = fmaf(a, w4.z, acc[o4 * 4 + 2]);
+              acc[o4 * 4 + 3] = fmaf(a, w4.w, acc[o4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(p.out + (size_t)gpix * COUT);
+#pragma unroll
+  for (int o4 = 0; o4 < COUT / 4; ++o4) dst[o4] = make_float4(acc[o4 * 4], acc[o4 * 4 + 1], acc[o4 * 4 + 2], acc[o4 * 4 + 3]);
+
+  // per-channel sum / sum of squares: warp shuffle tree, then one shared atomic per warp and channel
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float s = acc[o], q = acc[o] * acc[o];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, d);
+      q += __shfl_xor_sync(0xffffffffu, q, d);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_red[o], s);
+      atomicAdd(&s_red[COUT + o], q);
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * COUT) {
+    const int which = tid / COUT, c = tid - which * COUT;
+    atomicAdd(p.out_stats + ((size_t)n * COUT + c) * 2 + which, (double)s_red[tid]);
+  }
+}
+
+// land1/land2 [B,1,256,256] -> raw [2B,64,64,16] + stats; r0/r1 are workspace raws (with stats)
+int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
+                           const Raw& r0, const Raw& r1, const Raw& r2, int B, cudaStream_t st) {
+  AP_REQUIRE(r0.B == 2 * B && r1.B == 2 * B && r2.B == 2 * B, AP_ERR_INVALID, "landmark: workspace batch");
+  LandP a{land1, land2, nullptr, w0, r0.p, r0.stats, B, 256, 256};
+  land_conv_kernel<1, 8, 1><<<2 * B * 65536 / 256, 256, 0, st>>>(a);
+  AP_CUDA(cudaGetLastError());
+  LandP b{r0.p, nullptr, r0.stats, w1, r1.p, r1.stats, B, 256, 128};
+  land_conv_kernel<8, 16, 2><<<2 * B * 16384 / 256, 256, 0, st>>>(b);
+  AP_CUDA(cudaGetLastError());
+  LandP c{r1.p, nullptr, r1.stats, w2, r2.p, r2.stats, B, 128, 64};
+  land_conv_kernel<16, 16, 2><<<2 * B * 4096 / 256, 256, 0, st>>>(c);
+  AP_CUDA(cudaGetLastError());
+  launches_add(3);
+  return AP_OK;
+}
+
+}  // namespace ap

@@ -360,21 +360,26 @@ int Runner::run(const Inputs& in) {
   AP_TRY(apply(rM, 0, 256, 0, &XL, 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
   tap_f32("merge", xres[0], B, 64, 64, 256);
 
-  // ---- landmark branch, twice (networks.py:1280-1282, 1331-1332) ----
-  for (int li = 0; li < 2; ++li) {
-    const float* land = li == 0 ? in.land1 : in.land2;
-    Raw rl0 = raw(B, 256, 256, 8, true);
-    AP_TRY(conv_thin(geom_conv(B, 256, 1, 8, 3, 1, 1, 0), land, 1, 1, W("model_landmark_trans.0").simt, rl0));
-    Act L0 = act(B, 256, 256, 8, 0, FMT_F32);
-    AP_TRY(apply(rl0, 0, 8, 1, &L0, 0, 0));
-    Raw rl1 = raw(B, 128, 128, 16, true);
-    AP_TRY(conv_thin(geom_conv(B, 256, 8, 16, 3, 2, 1, 0), (const float*)L0.p0, 0, 8, W("model_landmark_trans.3").simt, rl1));
-    Act L1 = act(B, 128, 128, 16, 0, FMT_F32);
-    AP_TRY(apply(rl1, 0, 16, 1, &L1, 0, 0));
-    Raw rl2 = raw(B, 64, 64, 16, true);
-    AP_TRY(conv_thin(geom_conv(B, 128, 16, 16, 3, 2, 1, 0), (const float*)L1.p0, 0, 16, W("model_landmark_trans.6").simt, rl2));
-    AP_TRY(apply(rl2, 0, 16, 0, &XL, 256 + 16 * li, 1));
-    tap_act(li == 0 ? "land1" : "land2", XL, 256 + 16 * li, 16);
+  // ---- landmark branch on land1 and land2 as one batch of 2B maps (networks.py:1280-1282, 1331-1332) ----
+  {
+    Raw rl0 = raw(2 * B, 256, 256, 8, true);
+    Raw rl1 = raw(2 * B, 128, 128, 16, true);
+    Raw rl2 = raw(2 * B, 64, 64, 16, true);
+    if (ph == PH_EXEC) {
+      AP_TRY(launch_landmark_branch(in.land1, in.land2, W("model_landmark_trans.0").simt, W("model_landmark_trans.3").simt,
+                                    W("model_landmark_trans.6").simt, rl0, rl1, rl2, B, st));
+      AP_TRY(mark(CL_LAND, 2.0 * 2 * B * 9.0 * (65536.0 * 8 + 16384.0 * 8 * 16 + 4096.0 * 16 * 16)));
+    }
+    for (int li = 0; li < 2; ++li) {
+      Raw v = rl2;  // view of this landmark's half of the batch
+      v.B = B;
+      if (ph != PH_SIZE) {
+        v.p = rl2.p + (size_t)li * B * 64 * 64 * 16;
+        v.stats = rl2.stats + (size_t)li * B * 16 * 2;
+      }
+      AP_TRY(apply(v, 0, 16, 0, &XL, 256 + 16 * li, 1));
+      tap_act(li == 0 ? "land1" : "land2", XL, 256 + 16 * li, 16);
+    }
   }
 
   // ---- 9 residual blocks (networks.py:1333-1337, 2303-2421) ----

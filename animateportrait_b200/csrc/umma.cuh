@@ -118,4 +118,42 @@ static __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, 
 static __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 static __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- TMA tensor store (shared -> global), bulk-group completion ----
+static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+static __device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Epilogue building block, executed by ONE warp: 32 accumulator rows (lane = row) x 32 fp32 columns
+//   registers -> 128B-swizzled 4 KB staging slab -> one TMA store of the box {32 ch, 32 px, 1 row, 1 image}.
+// `slab_gen`/`slab_s` are the generic / shared-space addresses of this warp's slab (1024-B aligned);
+// `pending` = how many earlier stores of this warp may still be reading OTHER slabs (NSLAB - 1).
+template <int PENDING>
+static __device__ __forceinline__ void epi_store_block(const float (&v)[32], uint8_t* slab_gen, uint32_t slab_s, int lane,
+                                                       const CUtensorMap* omap, int c, int x, int y, int n) {
+  if (lane == 0) bulk_wait_read<PENDING>();  // the store that last used this slab has finished reading it
+  __syncwarp();
+  uint8_t* rowp = slab_gen + lane * 128;
+  const int r8 = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(rowp + ((j ^ r8) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(omap, slab_s, c, x, y, n);
+    bulk_commit();
+  }
+}
+
 }  // namespace ap
