@@ -188,14 +188,15 @@ int launch_conv_simt(const SimtConvP& p, cudaStream_t st) {
 // thin for tensor cores.  CTA = 32x32 output pixels, 128 threads; each thread owns one column of
 // 8 output rows so that a 14-row input column and the 7 ky weights are loaded once per (kx, channel
 // quad) and reused for 8 x 7 x 4 FMAs.  The 38x38 input patch is staged 8 channels at a time with the
-// preceding InstanceNorm + ReLU applied; pixel stride 12 floats keeps the float4 reads conflict-free.
+// preceding InstanceNorm + ReLU applied (4 channels at a time measured slower: half-sector global reads);
+// pixel stride 12 floats keeps the float4 reads conflict-free.
 // --------------------------------------------------------------------------------------------
 constexpr int OC_T = 32, OC_P = OC_T + 6, OC_CG = 8, OC_CS = 12, OC_ROWS = 8;
 
 template <int ONC>
 __global__ void __launch_bounds__(128) out_conv_kernel(const OutConvP p) {
   extern __shared__ __align__(16) float sm[];
-  float* tile = sm;                           // [38*38][12]
+  float* tile = sm;                           // [38*38][OC_CS]
   float* wsm = tile + OC_P * OC_P * OC_CS;    // [ONC][49][64]
   float* mean = wsm + ONC * 49 * 64;          // [64]
   float* rstd = mean + 64;                    // [64]
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const OutConvP p) {
 
   for (int c0 = 0; c0 < 64; c0 += OC_CG) {
     __syncthreads();  // previous group fully consumed (and, first time, mean/rstd/weights visible)
-    for (int i = tid; i < OC_P * OC_P * 2; i += 128) {
-      const int pp = i >> 1, cq = (i & 1) * 4;
+    for (int i = tid; i < OC_P * OC_P * (OC_CG / 4); i += 128) {
+      const int pp = i / (OC_CG / 4), cq = (i % (OC_CG / 4)) * 4;
       const int py = pp / OC_P, px = pp - py * OC_P;
       const int iy = reflect_idx(y0 + py - 3, S), ix = reflect_idx(x0 + px - 3, S);
       float4 v = __ldg(reinterpret_cast<const float4*>(p.raw + ((size_t)(n * S + iy) * S + ix) * 64 + c0 + cq));

@@ -177,22 +177,46 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
     const int r8 = row & 7;
     const int atom_off = (row >> 3) * 1024 + r8 * 128;
     const uint32_t* pbase = patch + yy * ST_PW + xx;
-    for (int it = 0; it < ntiles; ++it) {
-      const int t = t_begin + it;
+    // per-thread patch elements: idx = row + 128*k, k < 14 (1680 words); (ch, py, px) are tile-independent
+    constexpr int NPRE = (ST_PATCH + 127) / 128;
+    int pch[NPRE];  // ch*65536 | py<<8 | px  packed
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int idx = row + 128 * k;
+      const int ch = idx / (ST_PH * ST_PW);
+      const int r = idx - ch * (ST_PH * ST_PW);
+      const int py = r / ST_PW, px = r - py * ST_PW;
+      pch[k] = (idx < ST_PATCH) ? ((ch << 16) | (py << 8) | px) : -1;
+    }
+    float pre[NPRE];
+    auto prefetch = [&](int t) {
       const int img = t >> 9, rem = t & 511;
       const int y0 = (rem >> 2) * 2, x0 = (rem & 3) * 64;
-      if (it > 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the old patch
       const float* src = p.in + (size_t)img * 3 * 65536;
-      for (int idx = row; idx < ST_PATCH; idx += 128) {
-        const int ch = idx / (ST_PH * ST_PW);
-        const int r = idx - ch * (ST_PH * ST_PW);
-        const int py = r / ST_PW, px = r - py * ST_PW;
-        const float v = __ldg(src + ch * 65536 + st_reflect(y0 - 3 + py) * 256 + st_reflect(x0 - 3 + px));
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-        patch[idx] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        pre[k] = 0.f;
+        if (pch[k] >= 0) {
+          const int ch = pch[k] >> 16, py = (pch[k] >> 8) & 255, px = pch[k] & 255;
+          pre[k] = __ldg(src + ch * 65536 + st_reflect(y0 - 3 + py) * 256 + st_reflect(x0 - 3 + px));
+        }
+      }
+    };
+    if (ntiles > 0) prefetch(t_begin);
+    for (int it = 0; it < ntiles; ++it) {
+      if (it > 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the old patch
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        if (pch[k] >= 0) {
+          const float v = pre[k];
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+          patch[row + 128 * k] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // the next tile's patch loads fly while this tile's chunks are built
+      if (it + 1 < ntiles) prefetch(t_begin + it + 1);
       // chunk c is built in slot c & 1: chunk 0 reuses the slot of the previous tile's chunk 2,
       // chunk 1 the slot of the previous tile's chunk 1, chunk 2 the slot of this tile's chunk 0
       const uint32_t par = ((uint32_t)it & 1u) ^ 1u;

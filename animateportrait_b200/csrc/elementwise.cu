@@ -58,69 +58,92 @@ __device__ __forceinline__ void stats_to_affine(const double* st, int n, int sta
   const double su = st[((size_t)n * stat_C + stat_coff + c) * 2 + 0];
   const double sq = st[((size_t)n * stat_C + stat_coff + c) * 2 + 1];
   const double m = su * inv_n;
-  double var = sq * inv_n - m * m;
+  double var = sq * inv_n - m * m;  // sums are exact enough in double; the reference's own IN is fp32
   if (var < 0.0) var = 0.0;
   *mean = (float)m;
-  *rstd = (float)(1.0 / sqrt(var + 1e-5));  // eps of nn.InstanceNorm2d (networks.py:34)
+  *rstd = 1.0f / sqrtf((float)var + 1e-5f);  // eps of nn.InstanceNorm2d (networks.py:34)
 }
 
 // ------------------------------------------------------------------------------------------------
 // apply: y = IN(raw) [+ IN(raw2)] [+ bias] [+ res_in], optional ReLU; -> res_out (fp32) and/or dst.
-// grid (pixel chunks, B); each thread handles 4 channels of one pixel per iteration.
+// grid (pixel chunks, B).  TPP = C/4 threads per pixel: a thread keeps ONE channel quad (its mean / rstd
+// live in registers) and walks pixels, four at a time so that 4-12 independent 16-byte loads are in
+// flight per thread.  H and W are powers of two (64/128/256): no integer division anywhere.
 // ------------------------------------------------------------------------------------------------
-constexpr int APPLY_PIX_PER_CTA = 128;
 
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+template <int TPP>
 __global__ void __launch_bounds__(256) apply_kernel(const ApplyP p) {
-  __shared__ float s_mean[256], s_rstd[256], s_mean2[256], s_rstd2[256];
+  constexpr int NY = 256 / TPP;  // pixels per pass
+  constexpr int APPLY_PIX_PER_CTA = (4 * NY > 128) ? 4 * NY : 128;
   const int n = blockIdx.y;
-  const int tid = threadIdx.x;
-  const double inv_n = 1.0 / (double)(p.H * p.W);
-  for (int c = tid; c < p.C; c += 256) {
-    if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c, inv_n, &s_mean[c], &s_rstd[c]);
-    else { s_mean[c] = p.bias ? -p.bias[c] : 0.f; s_rstd[c] = 1.f; }
-    if (p.raw2) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c, inv_n, &s_mean2[c], &s_rstd2[c]);
-  }
-  __syncthreads();
-  Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
-  const int tpp = p.C >> 2;  // threads per pixel
+  const int cq = threadIdx.x % TPP, py = threadIdx.x / TPP;
+  const int c = cq * 4;
   const int HW = p.H * p.W;
-  const int pix0 = blockIdx.x * APPLY_PIX_PER_CTA;
-  const int pix1 = min(pix0 + APPLY_PIX_PER_CTA, HW);
-  for (int i = tid; i < (pix1 - pix0) * tpp; i += 256) {
-    const int pix = pix0 + i / tpp;
-    const int c = (i % tpp) * 4;
-    const size_t gp = (size_t)n * HW + pix;
-    float4 v = *reinterpret_cast<const float4*>(p.raw + gp * p.raw_C + p.raw_coff + c);
-    v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
-    v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
-    v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
-    v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
-    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (p.raw2) {
-      const float4 u = *reinterpret_cast<const float4*>(p.raw2 + gp * p.raw2_C + p.raw2_coff + c);
-      v.x += (u.x - s_mean2[c + 0]) * s_rstd2[c + 0];
-      v.y += (u.y - s_mean2[c + 1]) * s_rstd2[c + 1];
-      v.z += (u.z - s_mean2[c + 2]) * s_rstd2[c + 2];
-      v.w += (u.w - s_mean2[c + 3]) * s_rstd2[c + 3];
+  const int logW = 31 - __clz(p.W);
+  float mean[4], rstd[4], mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const double inv_n = 1.0 / (double)HW;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
+      else { mean[e] = p.bias ? -p.bias[c + e] : 0.f; rstd[e] = 1.f; }
+      if (p.raw2) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
     }
-    if (p.res_in) {
-      const float4 r = *reinterpret_cast<const float4*>(p.res_in + gp * p.C + c);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  }
+  Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
+  const int pix0 = blockIdx.x * APPLY_PIX_PER_CTA + py;
+  const float* raw = p.raw + ((size_t)n * HW) * p.raw_C + p.raw_coff + c;
+  const float* raw2 = p.raw2 ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
+  const float* rin = p.res_in ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
+  float* rout = p.res_out ? p.res_out + ((size_t)n * HW) * p.C + c : nullptr;
+#pragma unroll 1
+  for (int k0 = 0; k0 < APPLY_PIX_PER_CTA; k0 += 4 * NY) {
+    float4 v[4], u[4], r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pix = pix0 + k0 + j * NY;
+      v[j] = ld_stream(raw + (size_t)pix * p.raw_C);
+      if (raw2) u[j] = ld_stream(raw2 + (size_t)pix * p.raw2_C);
+      if (rin) r[j] = ld_stream(rin + (size_t)pix * p.C);
     }
-    if (p.res_out) *reinterpret_cast<float4*>(p.res_out + gp * p.C + c) = v;
-    if (p.fmt >= 0) {
-      const int y = pix / p.W, x = pix - y * p.W;
-      store_pixel(d, n, y, x, c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pix = pix0 + k0 + j * NY;
+      float4 o;
+      o.x = (v[j].x - mean[0]) * rstd[0];
+      o.y = (v[j].y - mean[1]) * rstd[1];
+      o.z = (v[j].z - mean[2]) * rstd[2];
+      o.w = (v[j].w - mean[3]) * rstd[3];
+      if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (raw2) {
+        o.x += (u[j].x - mean2[0]) * rstd2[0];
+        o.y += (u[j].y - mean2[1]) * rstd2[1];
+        o.z += (u[j].z - mean2[2]) * rstd2[2];
+        o.w += (u[j].w - mean2[3]) * rstd2[3];
+      }
+      if (rin) { o.x += r[j].x; o.y += r[j].y; o.z += r[j].z; o.w += r[j].w; }
+      if (rout) *reinterpret_cast<float4*>(rout + (size_t)pix * p.C) = o;
+      if (p.fmt >= 0) store_pixel(d, n, pix >> logW, pix & (p.W - 1), c, o);
     }
   }
 }
 
 int launch_apply(const ApplyP& p, cudaStream_t st) {
-  AP_REQUIRE(p.C % 4 == 0 && p.C <= 256, AP_ERR_INVALID, "apply: C=%d must be a multiple of 4 and <= 256", p.C);
+  AP_REQUIRE(p.C == 16 || p.C == 128 || p.C == 256, AP_ERR_INVALID, "apply: C=%d (16, 128 or 256)", p.C);
   AP_REQUIRE(p.raw_C % 4 == 0 && p.raw_coff % 4 == 0, AP_ERR_INVALID, "apply: raw channel layout not 16B aligned");
   AP_REQUIRE(p.fmt < 0 || (p.dC % 4 == 0 && p.dcoff % 4 == 0), AP_ERR_INVALID, "apply: dst channel layout");
-  dim3 grid((p.H * p.W + APPLY_PIX_PER_CTA - 1) / APPLY_PIX_PER_CTA, p.B);
-  apply_kernel<<<grid, 256, 0, st>>>(p);
+  const int ppc = (p.C == 16) ? 256 : 128;  // pixels per CTA (matches APPLY_PIX_PER_CTA in the kernel)
+  AP_REQUIRE((p.W & (p.W - 1)) == 0 && (p.H * p.W) % ppc == 0, AP_ERR_INVALID, "apply: %dx%d", p.H, p.W);
+  dim3 grid(p.H * p.W / ppc, p.B);
+  if (p.C == 256) apply_kernel<64><<<grid, 256, 0, st>>>(p);
+  else if (p.C == 128) apply_kernel<32><<<grid, 256, 0, st>>>(p);
+  else apply_kernel<4><<<grid, 256, 0, st>>>(p);
   AP_CUDA(cudaGetLastError());
   launches_add(1);
   return AP_OK;
@@ -130,6 +153,11 @@ int launch_apply(const ApplyP& p, cudaStream_t st) {
 // double feature warp (networks.py:1298-1313 + intrinsic_flow_models/modules.py:596-625).
 // Arithmetic follows oracle/netg_oracle.py::double_feature_warping_closed_form in
 // PyTorch's op order; __f*_rn intrinsics keep nvcc from contracting the coordinate math into FMAs.
+// A CTA owns 64 consecutive pixels of one image.  Phase 1: one thread per (pixel, warp kind) computes
+// the four bilinear tap offsets and weights ONCE (level > 0 also interpolates the 256x256 conditioning
+// maps, align_corners=True) into shared memory.  Phase 2: all threads gather with a (pixel, channel quad)
+// mapping -- 16-byte loads, the producer's InstanceNorm + ReLU applied on the fly -- and write both
+// halves of the channel concat.
 // ------------------------------------------------------------------------------------------------
 struct Lerp { int i0, i1; float l0, l1; };
 
@@ -179,81 +207,117 @@ __device__ __forceinline__ Taps4 make_taps4(float ix, float iy, int S) {
   return t;
 }
 
+constexpr int WARP_PIX = 64;  // pixels per CTA
+
+template <int TPP>
 __global__ void __launch_bounds__(256) warp_kernel(const WarpP p) {
-  __shared__ float s_mean[128], s_rstd[128];
+  __shared__ int s_off[2][4][WARP_PIX];
+  __shared__ float s_w[2][4][WARP_PIX];
+  __shared__ int s_keep[WARP_PIX];
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  const int S = p.S, C = p.C;
-  const double inv_n = 1.0 / (double)(S * S);
-  for (int c = tid; c < C; c += 256) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c, inv_n, &s_mean[c], &s_rstd[c]);
+  const int S = p.S;
+  constexpr int C = TPP * 4;
+  const int pix_base = blockIdx.x * WARP_PIX;
+
+  // ---- phase 1: tap tables ----
+  if (tid < 2 * WARP_PIX) {
+    const int kind = tid >> 6, lp = tid & (WARP_PIX - 1);  // kind 0: motion warp, 1: flow warp (+ mask)
+    const int pix = pix_base + lp;
+    const int logS = 31 - __clz(S);
+    const int i = pix >> logS, j = pix & (S - 1);
+    const float* mo = p.motion + (size_t)n * 256 * 256 * 2;
+    const float* fl = p.flow + (size_t)n * 2 * 256 * 256;
+    const float* ms = p.ifmask + (size_t)n * 256 * 256;
+    Lerp ly{}, lx{};
+    if (p.level > 0) {
+      const float scale = 255.f / (float)(S - 1);  // fp32((in-1)/(out-1))
+      ly = src_index_ac_true(i, scale, 256);
+      lx = src_index_ac_true(j, scale, 256);
+    }
+    Taps4 t;
+    if (kind == 0) {
+      // motion warp: F.grid_sample(x, motion) with default align_corners=False
+      float mx, my;
+      if (p.level == 0) { mx = mo[(size_t)pix * 2 + 0]; my = mo[(size_t)pix * 2 + 1]; }
+      else { mx = bilerp(mo + 0, 2, 256, ly, lx); my = bilerp(mo + 1, 2, 256, ly, lx); }
+      t = make_taps4(unnormalize_ac_false(mx, S), unnormalize_ac_false(my, S), S);
+    } else {
+      float fx, fy, mk;
+      if (p.level == 0) { fx = fl[pix]; fy = fl[256 * 256 + pix]; mk = ms[pix]; }
+      else {
+        const float fs = (p.level == 1) ? 0.5f : 0.25f;  // flow / 2**level before the resize (exact)
+        // scaling by a power of two commutes exactly with the interpolation arithmetic
+        fx = bilerp(fl, 1, 256, ly, lx) * fs;
+        fy = bilerp(fl + 256 * 256, 1, 256, ly, lx) * fs;
+        mk = bilerp(ms, 1, 256, ly, lx);
+      }
+      // flow warp: grid = 2*(j + f)/(S-1) - 1, then the same un-normalisation
+      const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)j, fx)), (float)(S - 1)), 1.f);
+      const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)i, fy)), (float)(S - 1)), 1.f);
+      t = make_taps4(unnormalize_ac_false(gx, S), unnormalize_ac_false(gy, S), S);
+      s_keep[lp] = (mk > 0.5f) ? 1 : 0;  // torch.where(mask > 0.5, out, -1)
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_off[kind][k][lp] = t.off[k]; s_w[kind][k][lp] = t.w[k]; }
+  }
+  // ---- per-thread channel quad: mean / rstd of the producer's InstanceNorm ----
+  const int cq = tid % TPP, py = tid / TPP;
+  const int c = cq * 4;
+  float mean[4], rstd[4];
+  {
+    const double inv_n = 1.0 / (double)(S * S);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
+  }
   __syncthreads();
 
-  const int tpp = C >> 2;
-  const int ppc = 256 / tpp;  // pixels per CTA iteration
-  const int pix = blockIdx.x * ppc + tid / tpp;
-  if (pix >= S * S) return;
-  const int c = (tid % tpp) * 4;
-  const int i = pix / S, j = pix - i * S;
-
-  // conditioning at this pixel (level > 0: bilinear resize of the 256x256 maps, align_corners=True)
-  float mx, my, fx, fy, mk;
-  const float* mo = p.motion + (size_t)n * 256 * 256 * 2;
-  const float* fl = p.flow + (size_t)n * 2 * 256 * 256;
-  const float* ms = p.ifmask + (size_t)n * 256 * 256;
-  if (p.level == 0) {
-    mx = mo[(size_t)pix * 2 + 0]; my = mo[(size_t)pix * 2 + 1];
-    fx = fl[pix]; fy = fl[256 * 256 + pix];
-    mk = ms[pix];
-  } else {
-    const float scale = 255.f / (float)(S - 1);  // fp32((in-1)/(out-1))
-    const Lerp ly = src_index_ac_true(i, scale, 256), lx = src_index_ac_true(j, scale, 256);
-    mx = bilerp(mo + 0, 2, 256, ly, lx);
-    my = bilerp(mo + 1, 2, 256, ly, lx);
-    const float fs = (p.level == 1) ? 0.5f : 0.25f;  // flow / 2**level before the resize (exact)
-    // scaling by a power of two commutes exactly with the interpolation arithmetic
-    fx = bilerp(fl, 1, 256, ly, lx) * fs;
-    fy = bilerp(fl + 256 * 256, 1, 256, ly, lx) * fs;
-    mk = bilerp(ms, 1, 256, ly, lx);
-  }
-  // motion warp: F.grid_sample(x, motion) with default align_corners=False
-  const Taps4 tm = make_taps4(unnormalize_ac_false(mx, S), unnormalize_ac_false(my, S), S);
-  // flow warp: grid = 2*(j + f)/(S-1) - 1, then the same un-normalisation
-  const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)j, fx)), (float)(S - 1)), 1.f);
-  const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)i, fy)), (float)(S - 1)), 1.f);
-  const Taps4 tf = make_taps4(unnormalize_ac_false(gx, S), unnormalize_ac_false(gy, S), S);
-
-  const float4 mean = *reinterpret_cast<const float4*>(&s_mean[c]);
-  const float4 rstd = *reinterpret_cast<const float4*>(&s_rstd[c]);
+  // ---- phase 2: gather ----
+  constexpr int NY = 256 / TPP;
   const float* src = p.raw + (size_t)n * S * S * p.raw_C + p.raw_coff + c;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    if (tm.off[t] >= 0) {
-      float4 v = *reinterpret_cast<const float4*>(src + (size_t)tm.off[t] * p.raw_C);
-      v.x = fmaxf((v.x - mean.x) * rstd.x, 0.f); v.y = fmaxf((v.y - mean.y) * rstd.y, 0.f);
-      v.z = fmaxf((v.z - mean.z) * rstd.z, 0.f); v.w = fmaxf((v.w - mean.w) * rstd.w, 0.f);
-      a.x = fmaf(v.x, tm.w[t], a.x); a.y = fmaf(v.y, tm.w[t], a.y);
-      a.z = fmaf(v.z, tm.w[t], a.z); a.w = fmaf(v.w, tm.w[t], a.w);
-    }
-    if (tf.off[t] >= 0) {
-      float4 v = *reinterpret_cast<const float4*>(src + (size_t)tf.off[t] * p.raw_C);
-      v.x = fmaxf((v.x - mean.x) * rstd.x, 0.f); v.y = fmaxf((v.y - mean.y) * rstd.y, 0.f);
-      v.z = fmaxf((v.z - mean.z) * rstd.z, 0.f); v.w = fmaxf((v.w - mean.w) * rstd.w, 0.f);
-      b.x = fmaf(v.x, tf.w[t], b.x); b.y = fmaf(v.y, tf.w[t], b.y);
-      b.z = fmaf(v.z, tf.w[t], b.z); b.w = fmaf(v.w, tf.w[t], b.w);
-    }
-  }
-  if (!(mk > 0.5f)) b = make_float4(-1.f, -1.f, -1.f, -1.f);  // torch.where(mask > 0.5, out, -1)
+  const int logS = 31 - __clz(S);
   Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, S, S, 0};
-  store_pixel(d, n, i, j, c, a);
-  store_pixel(d, n, i, j, C + c, b);
+#pragma unroll 1
+  for (int lp = py; lp < WARP_PIX; lp += NY) {
+    float4 val[2][4];
+    float wt[2][4];
+#pragma unroll
+    for (int kind = 0; kind < 2; ++kind)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int off = s_off[kind][k][lp];
+        wt[kind][k] = s_w[kind][k][lp];
+        val[kind][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (off >= 0) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)off * p.raw_C));
+          v.x = fmaxf((v.x - mean[0]) * rstd[0], 0.f); v.y = fmaxf((v.y - mean[1]) * rstd[1], 0.f);
+          v.z = fmaxf((v.z - mean[2]) * rstd[2], 0.f); v.w = fmaxf((v.w - mean[3]) * rstd[3], 0.f);
+          val[kind][k] = v;
+        }
+      }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a.x = fmaf(val[0][k].x, wt[0][k], a.x); a.y = fmaf(val[0][k].y, wt[0][k], a.y);
+      a.z = fmaf(val[0][k].z, wt[0][k], a.z); a.w = fmaf(val[0][k].w, wt[0][k], a.w);
+      b.x = fmaf(val[1][k].x, wt[1][k], b.x); b.y = fmaf(val[1][k].y, wt[1][k], b.y);
+      b.z = fmaf(val[1][k].z, wt[1][k], b.z); b.w = fmaf(val[1][k].w, wt[1][k], b.w);
+    }
+    if (!s_keep[lp]) b = make_float4(-1.f, -1.f, -1.f, -1.f);
+    const int pix = pix_base + lp;
+    const int i = pix >> logS, j = pix & (S - 1);
+    store_pixel(d, n, i, j, c, a);
+    store_pixel(d, n, i, j, C + c, b);
+  }
 }
 
 int launch_warp(const WarpP& p, cudaStream_t st) {
   AP_REQUIRE(p.C == 32 || p.C == 64 || p.C == 128, AP_ERR_INVALID, "warp: C=%d", p.C);
-  const int tpp = p.C / 4, ppc = 256 / tpp;
-  dim3 grid((p.S * p.S + ppc - 1) / ppc, p.B);
-  warp_kernel<<<grid, 256, 0, st>>>(p);
+  AP_REQUIRE((p.S & (p.S - 1)) == 0 && (p.S * p.S) % WARP_PIX == 0, AP_ERR_INVALID, "warp: S=%d", p.S);
+  dim3 grid(p.S * p.S / WARP_PIX, p.B);
+  if (p.C == 32) warp_kernel<8><<<grid, 256, 0, st>>>(p);
+  else if (p.C == 64) warp_kernel<16><<<grid, 256, 0, st>>>(p);
+  else warp_kernel<32><<<grid, 256, 0, st>>>(p);
   AP_CUDA(cudaGetLastError());
   launches_add(1);
   return AP_OK;

@@ -7,25 +7,29 @@
 // the PREVIOUS layer is applied while the taps are loaded (raw conv outputs + per-(n,c) sums are what
 // travels through HBM, each tensor written once and read once); zero padding is applied after the
 // normalisation, as in the reference.  Biases cancel in the affine-less InstanceNorm.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace ap {
 
 void launches_add(int n);
 
+// The weights travel BY VALUE in the kernel parameters ([9][CIN][COUT] fp32, at most 9 KB): with the tap /
+// channel loops fully unrolled every FMA reads its weight straight from the constant bank, no load at all.
+template <int CIN, int COUT>
 struct LandP {
   const float* in0;   // CIN == 1: land1 [B,1,256,256];  else raw NHWC [2B,Hin,Win,CIN]
   const float* in1;   // CIN == 1: land2
   const double* in_stats;  // [2B][CIN][2] (CIN > 1)
-  const float* w;     // [9][CIN][COUT] fp32
   float* out;         // raw NHWC [2B,Hout,Wout,COUT]
   double* out_stats;  // [2B][COUT][2]
   int B, Hin, Hout;
+  float w[9 * CIN * COUT];
 };
 
 template <int CIN, int COUT, int STRIDE>
-__global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
-  __shared__ __align__(16) float sw[9 * CIN * COUT];
+__global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ LandP<CIN, COUT> p) {
   __shared__ float s_mean[CIN], s_rstd[CIN];
   __shared__ float s_red[2 * COUT];
   const int tid = threadIdx.x;
@@ -34,7 +38,6 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
   const int n = gpix / HWo;
   const int pix = gpix - n * HWo;
   const int oy = pix / p.Hout, ox = pix - oy * p.Hout;
-  for (int i = tid; i < 9 * CIN * COUT; i += 256) sw[i] = p.w[i];
   if (tid < 2 * COUT) s_red[tid] = 0.f;
   if (CIN > 1 && tid < CIN) {
     const double inv = 1.0 / (double)(p.Hin * p.Hin);
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
     double var = sq * inv - m * m;
     if (var < 0.0) var = 0.0;
     s_mean[tid] = (float)m;
-    s_rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
+    s_rstd[tid] = 1.0f / sqrtf((float)var + 1e-5f);
   }
   __syncthreads();
 
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
     for (int kx = 0; kx < 3; ++kx) {
       const int ix = ox * STRIDE + kx - 1;
       if (ix < 0 || ix >= p.Hin) continue;
-      const float* wt = sw + (ky * 3 + kx) * CIN * COUT;
+      const float* wt = p.w + (ky * 3 + kx) * CIN * COUT;
       if (CIN == 1) {
         const float* src = (n < p.B) ? p.in0 + (size_t)n * p.Hin * p.Hin : p.in1 + (size_t)(n - p.B) * p.Hin * p.Hin;
         const float v = __ldg(src + iy * p.Hin + ix);
@@ -77,13 +80,7 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
             const int c = c4 * 4 + e;
             const float a = fmaxf((v[e] - s_mean[c]) * s_rstd[c], 0.f);  // IN + ReLU of the previous layer
 #pragma unroll
-            for (int o4 = 0; o4 < COUT / 4; ++o4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wt + c * COUT + o4 * 4);
-              acc[o4 * 4 + 0] = fmaf(a, w4.x, acc[o4 * 4 + 0]);
-              acc[o4 * 4 + 1] = fmaf(a, w4.y, acc[o4 * 4 + 1]);
-              acc[o4 * 4 + 2] = fmaf(a, w4.z, acc[o4 * 4 + 2]);
-              acc[o4 * 4 + 3] = fmaf(a, w4.w, acc[o4 * 4 + 3]);
-            }
+            for (int o = 0; o < COUT; ++o) acc[o] = fmaf(a, wt[c * COUT + o], acc[o]);
           }
         }
       }
@@ -114,19 +111,29 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const LandP p) {
   }
 }
 
-// land1/land2 [B,1,256,256] -> raw [2B,64,64,16] + stats; r0/r1 are workspace raws (with stats)
+// land1/land2 [B,1,256,256] -> raw [2B,64,64,16] + stats; r0/r1 are workspace raws (with stats).
+// w0/w1/w2 are HOST arrays in [slab][Cin][Cout] order.
 int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
                            const Raw& r0, const Raw& r1, const Raw& r2, int B, cudaStream_t st) {
   AP_REQUIRE(r0.B == 2 * B && r1.B == 2 * B && r2.B == 2 * B, AP_ERR_INVALID, "landmark: workspace batch");
-  LandP a{land1, land2, nullptr, w0, r0.p, r0.stats, B, 256, 256};
-  land_conv_kernel<1, 8, 1><<<2 * B * 65536 / 256, 256, 0, st>>>(a);
-  AP_CUDA(cudaGetLastError());
-  LandP b{r0.p, nullptr, r0.stats, w1, r1.p, r1.stats, B, 256, 128};
-  land_conv_kernel<8, 16, 2><<<2 * B * 16384 / 256, 256, 0, st>>>(b);
-  AP_CUDA(cudaGetLastError());
-  LandP c{r1.p, nullptr, r1.stats, w2, r2.p, r2.stats, B, 128, 64};
-  land_conv_kernel<16, 16, 2><<<2 * B * 4096 / 256, 256, 0, st>>>(c);
-  AP_CUDA(cudaGetLastError());
+  {
+    LandP<1, 8> a{land1, land2, nullptr, r0.p, r0.stats, B, 256, 256, {}};
+    memcpy(a.w, w0, sizeof(a.w));
+    land_conv_kernel<1, 8, 1><<<2 * B * 65536 / 256, 256, 0, st>>>(a);
+    AP_CUDA(cudaGetLastError());
+  }
+  {
+    LandP<8, 16> b{r0.p, nullptr, r0.stats, r1.p, r1.stats, B, 256, 128, {}};
+    memcpy(b.w, w1, sizeof(b.w));
+    land_conv_kernel<8, 16, 2><<<2 * B * 16384 / 256, 256, 0, st>>>(b);
+    AP_CUDA(cudaGetLastError());
+  }
+  {
+    LandP<16, 16> c{r1.p, nullptr, r1.stats, r2.p, r2.stats, B, 128, 64, {}};
+    memcpy(c.w, w2, sizeof(c.w));
+    land_conv_kernel<16, 16, 2><<<2 * B * 4096 / 256, 256, 0, st>>>(c);
+    AP_CUDA(cudaGetLastError());
+  }
   launches_add(3);
   return AP_OK;
 }

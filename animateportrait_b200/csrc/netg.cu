@@ -65,6 +65,7 @@ struct LayerW {
   float* simt = nullptr;          // [slab][Cin][Cout]
   __nv_bfloat16* hi = nullptr;    // [slab][Cout][Cin]
   __nv_bfloat16* lo = nullptr;
+  std::vector<float> host;        // landmark layers: [slab][Cin][Cout] on the host (kernel-parameter weights)
 };
 
 struct TapRec {
@@ -84,12 +85,17 @@ struct Plan {
   // staging for ap_netg_forward_host
   float* h_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float* h_out = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_in[3] = {nullptr, nullptr, nullptr};
   ~Plan() {
     for (UmmaConv* c : convs) umma_conv_destroy(c);
     if (arena) cudaFree(arena);
     if (sarena) cudaFree(sarena);
     for (float* p : h_in) if (p) cudaFree(p);
     if (h_out) cudaFree(h_out);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_start) cudaEventDestroy(ev_start);
+    for (cudaEvent_t e : ev_in) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -137,6 +143,12 @@ struct Runner {
   Phase ph;
   cudaStream_t st;
   size_t off = 0, soff = 0, conv_i = 0;
+  const cudaEvent_t* in_ready = nullptr;  // host-buffer entry point: [0] photo, [1] motion/flow/ifmask, [2] land1/land2
+
+  int wait_input(int k) {
+    if (ph == PH_EXEC && in_ready) AP_CUDA(cudaStreamWaitEvent(st, in_ready[k], 0));
+    return AP_OK;
+  }
 
   void* alloc(size_t bytes) {
     off = align_up(off, 1024);
@@ -295,6 +307,7 @@ int Runner::run(const Inputs& in) {
 
   // ---- three 7x7 stems fused into one Cout=160 problem on the photo (networks.py:1218-1243) ----
   Raw stem = raw(B, 256, 256, 160, true);
+  AP_TRY(wait_input(0));
   if (prec == AP_PREC_FP32_SIMT) {
     AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
   } else if (ph == PH_EXEC) {
@@ -307,6 +320,7 @@ int Runner::run(const Inputs& in) {
 
   // ---- branch 1: warp L0 -> tri01 -> tri02 ----
   Act W0 = act(B, 256, 256, 64, 0, afmt);
+  AP_TRY(wait_input(1));
   AP_TRY(warp(stem, 0, 32, 0, in, W0, 0));
   tap_act("warp0", W0, 0, 64);
   Raw r01 = raw(B, 128, 128, 128, true);
@@ -365,9 +379,11 @@ int Runner::run(const Inputs& in) {
     Raw rl0 = raw(2 * B, 256, 256, 8, true);
     Raw rl1 = raw(2 * B, 128, 128, 16, true);
     Raw rl2 = raw(2 * B, 64, 64, 16, true);
+    AP_TRY(wait_input(2));
     if (ph == PH_EXEC) {
-      AP_TRY(launch_landmark_branch(in.land1, in.land2, W("model_landmark_trans.0").simt, W("model_landmark_trans.3").simt,
-                                    W("model_landmark_trans.6").simt, rl0, rl1, rl2, B, st));
+      AP_TRY(launch_landmark_branch(in.land1, in.land2, W("model_landmark_trans.0").host.data(),
+                                    W("model_landmark_trans.3").host.data(), W("model_landmark_trans.6").host.data(), rl0,
+                                    rl1, rl2, B, st));
       AP_TRY(mark(CL_LAND, 2.0 * 2 * B * 9.0 * (65536.0 * 8 + 16384.0 * 8 * 16 + 4096.0 * 16 * 16)));
     }
     for (int li = 0; li < 2; ++li) {
@@ -558,7 +574,27 @@ int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const floa
       LayerW lw;
       lw.cout = s.cout; lw.cin = s.cin; lw.k = s.k;
       const bool thin = s.name.rfind("model_landmark_trans", 0) == 0;
-      const bool simt = thin || h->prec == AP_PREC_FP32_SIMT;
+      if (thin) {
+        // tiny layers whose weights ride in the kernel parameters: keep a packed host copy
+        std::vector<float> tmp(elems);
+        const float* hsrc = ptrs[idx[s.name + ".weight"]];
+        if (on_device) {
+          if (cudaMemcpy(tmp.data(), hsrc, elems * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("copy of %s to the host failed", s.name.c_str());
+            rc = AP_ERR_CUDA;
+            break;
+          }
+          hsrc = tmp.data();
+        }
+        lw.host.resize(elems);
+        for (int sl = 0; sl < 9; ++sl)
+          for (int ci = 0; ci < s.cin; ++ci)
+            for (int co = 0; co < s.cout; ++co)
+              lw.host[((size_t)sl * s.cin + ci) * s.cout + co] = hsrc[((size_t)co * s.cin + ci) * 9 + sl];
+        h->w[s.name] = lw;
+        continue;
+      }
+      const bool simt = h->prec == AP_PREC_FP32_SIMT;
       if (simt) rc = dalloc(elems * 4, (void**)&lw.simt);
       if (rc == AP_OK && !simt) rc = dalloc(elems * 2, (void**)&lw.hi);
       if (rc == AP_OK && !simt && h->prec == AP_PREC_FP32X3) rc = dalloc(elems * 2, (void**)&lw.lo);
@@ -604,18 +640,12 @@ int ap_netg_workspace_bytes(ap_netg* h, int B, size_t* bytes) {
   return AP_OK;
 }
 
-int ap_netg_forward(ap_netg* h, int B, const float* input, const float* land1, const float* land2, const float* motion,
-                    const float* flow, const float* ifmask, float* out, void* cuda_stream) {
-  AP_REQUIRE(h != nullptr, AP_ERR_INVALID, "null handle");
-  AP_REQUIRE(h->loaded, AP_ERR_STATE, "forward before load_weights");
-  AP_REQUIRE(B >= 1, AP_ERR_INVALID, "B=%d", B);
-  AP_REQUIRE(input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "null tensor pointer");
-  AP_CUDA(cudaSetDevice(h->device));
+static int forward_impl(ap_netg* h, int B, const Inputs& in, cudaStream_t st, const cudaEvent_t* in_ready) {
   Plan* pl = nullptr;
   AP_TRY(get_plan(h, B, &pl));
   const int64_t before = launches_get();
-  Inputs in{input, land1, land2, motion, flow, ifmask, out};
-  Runner rx{h, pl, PH_EXEC, (cudaStream_t)cuda_stream};
+  Runner rx{h, pl, PH_EXEC, st};
+  rx.in_ready = in_ready;
   if (h->profiling) {
     if (h->ev.empty()) {
       cudaEvent_t e;
@@ -625,12 +655,23 @@ int ap_netg_forward(ap_netg* h, int B, const float* input, const float* land1, c
     h->ev_used = 0;
     h->ev_class.clear();
     h->ev_flops.clear();
-    AP_CUDA(cudaEventRecord(h->ev[0], (cudaStream_t)cuda_stream));
+    AP_CUDA(cudaEventRecord(h->ev[0], st));
   }
   AP_TRY(rx.run(in));
   h->last_launches = launches_get() - before;
   h->last_plan = pl;
   return AP_OK;
+}
+
+int ap_netg_forward(ap_netg* h, int B, const float* input, const float* land1, const float* land2, const float* motion,
+                    const float* flow, const float* ifmask, float* out, void* cuda_stream) {
+  AP_REQUIRE(h != nullptr, AP_ERR_INVALID, "null handle");
+  AP_REQUIRE(h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1, AP_ERR_INVALID, "B=%d", B);
+  AP_REQUIRE(input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "null tensor pointer");
+  AP_CUDA(cudaSetDevice(h->device));
+  Inputs in{input, land1, land2, motion, flow, ifmask, out};
+  return forward_impl(h, B, in, (cudaStream_t)cuda_stream, nullptr);
 }
 
 int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* land1, const float* land2,
@@ -644,12 +685,28 @@ int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* lan
   const size_t px = (size_t)B * 256 * 256;
   const size_t sz[6] = {px * 3, px, px, px * 2, px * 2, px};
   const float* src[6] = {input, land1, land2, motion, flow, ifmask};
-  for (int i = 0; i < 6; ++i) {
-    if (!pl->h_in[i]) AP_CUDA(cudaMalloc(&pl->h_in[i], sz[i] * sizeof(float)));
-    AP_CUDA(cudaMemcpyAsync(pl->h_in[i], src[i], sz[i] * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (!pl->copy_stream) {
+    AP_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    AP_CUDA(cudaEventCreateWithFlags(&pl->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) AP_CUDA(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+    for (int i = 0; i < 6; ++i) AP_CUDA(cudaMalloc(&pl->h_in[i], sz[i] * sizeof(float)));
+    AP_CUDA(cudaMalloc(&pl->h_out, px * h->onc * sizeof(float)));
   }
-  if (!pl->h_out) AP_CUDA(cudaMalloc(&pl->h_out, px * h->onc * sizeof(float)));
-  AP_TRY(ap_netg_forward(h, B, pl->h_in[0], pl->h_in[1], pl->h_in[2], pl->h_in[3], pl->h_in[4], pl->h_in[5], pl->h_out, st));
+  // The six uploads run on a side stream in the order the forward consumes them (photo -> stems,
+  // motion/flow/ifmask -> warps, landmarks -> landmark branch); the compute stream waits per group, so only
+  // the photo upload is exposed and the rest hides behind the stem / encoder kernels.
+  AP_CUDA(cudaEventRecord(pl->ev_start, st));
+  AP_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->ev_start, 0));
+  const int order[6] = {0, 3, 4, 5, 1, 2};
+  for (int k = 0; k < 6; ++k) {
+    const int i = order[k];
+    AP_CUDA(cudaMemcpyAsync(pl->h_in[i], src[i], sz[i] * sizeof(float), cudaMemcpyHostToDevice, pl->copy_stream));
+    if (k == 0) AP_CUDA(cudaEventRecord(pl->ev_in[0], pl->copy_stream));
+    if (k == 3) AP_CUDA(cudaEventRecord(pl->ev_in[1], pl->copy_stream));
+    if (k == 5) AP_CUDA(cudaEventRecord(pl->ev_in[2], pl->copy_stream));
+  }
+  Inputs in{pl->h_in[0], pl->h_in[1], pl->h_in[2], pl->h_in[3], pl->h_in[4], pl->h_in[5], pl->h_out};
+  AP_TRY(forward_impl(h, B, in, st, pl->ev_in));
   AP_CUDA(cudaMemcpyAsync(out, pl->h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, st));
   AP_CUDA(cudaStreamSynchronize(st));
   return AP_OK;

@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -133,7 +133,7 @@ def run_reference(args, rank):
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
-    ap_.add_argument("--steps", type=int, default=20)
+    ap_.add_argument("--steps", type=int, default=100)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap_.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
@@ -154,8 +154,8 @@ def main():
     import torch
     import torch.distributed as dist
     import animateportrait_b200 as ap
+    from animateportrait_b200 import synth as O  # seeded stand-in checkpoint + synthetic batches (product side)
     from animateportrait_b200.frames import render_frames_sharded
-    from oracle import netg_oracle as O  # input/weight recipes + cpu_baseline leg only
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the generator")
@@ -267,10 +267,19 @@ def main():
     trunk = prof_acc["trunk_conv3x3"]
     trunk_tflops = trunk["flops"] / (trunk["ms"] * 1e-3) / 1e12 if trunk["ms"] > 0 else 0.0
     nprod = {"fp32": 3, "bf16": 1, "fp32_simt": 0}[args.precision]
+    traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "trunk_traffic.json")
+    if nprod and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("batch") == B and tj.get("precision") == args.precision:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (3x3 s1 trunk convs @64x64, 22 launches/step)"
                 if nprod else "conv_simt_kernel (CUDA-core validation path)",
                 "achieved": trunk_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": trunk_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": trunk_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                "mma_tflops": trunk_tflops * max(nprod, 1),
+                "frac_of_mma_ceiling": trunk_tflops * max(nprod, 1) / peaks["bf16_tflops_sustained"],
                 "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": trunk["flops"] / max(trunk["launches"], 1),
                 "avg_launch_ms": trunk["ms"] / max(trunk["launches"], 1),

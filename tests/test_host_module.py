@@ -95,3 +95,46 @@ def test_install_patches_a_networks_namespace():
     norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
     net = fake.ResnetConditionTriGenerator32_full_ifw(3, 1, 64, norm_layer=norm, use_dropout=False, n_blocks=9, div=3, disp=3)
     assert isinstance(net, ap.ResnetConditionTriGenerator32_full_ifw) and net.precision == "bf16"
+
+
+def test_package_synthetic_workload_is_the_oracles_recipe():
+    """bench.py / smoke take weights and inputs from animateportrait_b200.synth (the product never imports the
+    oracle); the oracle's own copy must stay bit-identical."""
+    from animateportrait_b200 import synth as S
+    for onc in (1, 3):
+        a, b = S.make_state_dict(onc, seed=3, bias_std=0.1), O.make_state_dict(onc, seed=3, bias_std=0.1)
+        assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    for kind in ("smooth", "noise"):
+        x, y = S.make_inputs(2, seed=5, kind=kind), O.make_inputs(2, seed=5, kind=kind)
+        assert all(torch.equal(p, q) for p, q in zip(x, y))
+    assert S.flops_per_frame(1) == O.flops_per_frame(1) == 140125405184.0
+    assert S.flops_per_frame(3) == O.flops_per_frame(3)
+
+
+REF_MODULE2 = "/root/reference/Module2"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_MODULE2), reason="reference tree not present (GPU box)")
+def test_sitecustomize_shim_swaps_the_class_inside_the_reference_define_G():
+    """The drop-in boundary, end to end on the host side: a fresh interpreter with the shim on PYTHONPATH imports
+    the UNMODIFIED reference `models.networks`; its own define_G (networks.py:175-176) then builds the B200 module,
+    and a checkpoint in the reference layout loads through load_state_dict."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from models import networks\n"
+        "import animateportrait_b200 as ap\n"
+        "net = networks.define_G(3, 1, 64, 'resnet_9blocks_rcatland32_full_ifw', 'instance', False, 'normal', 0.02, [], div=3, disp=3)\n"
+        "assert isinstance(net, ap.ResnetConditionTriGenerator32_full_ifw), type(net)\n"
+        "from animateportrait_b200 import synth\n"
+        "r = net.load_state_dict(synth.make_state_dict(1, seed=2))\n"
+        "assert not r.missing_keys and not r.unexpected_keys\n"
+        "other = networks.define_G(3, 1, 64, 'resnet_9blocks', 'instance')\n"
+        "assert type(other).__name__ == 'ResnetGenerator'\n"
+        "print('SHIM_OK', len(net.state_dict()))\n" % REF_MODULE2)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "animateportrait_b200", "shim"), root]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=REF_MODULE2, timeout=300)
+    assert "SHIM_OK 74" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
