@@ -22,6 +22,7 @@
 //   TMA-store the {32 ch, 32 px} box (coalesced, asynchronous), and reduce per-channel sum /
 //   sum-of-squares for the following InstanceNorm with a 31-shuffle butterfly per 32 columns.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -42,12 +43,15 @@ struct alignas(64) UmmaParams {
   int out_coff;
   double* stats;
   int stat_C, stat_coff;
-  int n_full, split, n_items;  // item list: n_full full tiles, then (tiles - n_full) * split N-parts
+  // item list in units of tile GROUPS (CG consecutive 128-pixel tiles, one per CTA of the pair):
+  // n_full whole groups with bn = Cout, then (groups - n_full) * split N-parts
+  int n_full, split, n_items;
+  int dbg;  // timing diagnostics only (AP_UMMA_DBG): 1 = no TMA loads after the first fill, 2 = no output stores, 4 = no statistics
 };
 
 struct UmmaConv {
   UmmaParams p;
-  int BN, nprod;
+  int BN, nprod, cg;
   dim3 grid;
   size_t smem;
 };
@@ -56,10 +60,13 @@ constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 constexpr int EPI_SLABS = 2;             // staging slabs per epilogue warp
 constexpr int EPI_BYTES = 4 * EPI_SLABS * 4096;
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, int CG>
 struct UmmaCfg {
-  static constexpr int W_TILE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (A_TILE_BYTES + W_TILE_BYTES);
+  static constexpr int PLANES = (NPROD == 3 ? 2 : 1);
+  static constexpr int W_ROWS = BN / CG;                     // rows of the weight tile this CTA stages
+  static constexpr int W_BOX = W_ROWS < 64 ? W_ROWS : 64;    // rows per TMA box
+  static constexpr int W_TILE_BYTES = W_ROWS * 128;
+  static constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
   static constexpr int STAGES_RAW = (226 * 1024 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256;
@@ -69,16 +76,17 @@ struct Item {
   int img, ty, tx, n0, bn;
 };
 
-__device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int BN) {
-  int m, n0 = 0, bn = BN;
+__device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int BN, int CG, int rank) {
+  int g, n0 = 0, bn = BN;
   if (item < p.n_full) {
-    m = item;
+    g = item;
   } else {
     const int r = item - p.n_full;
-    m = p.n_full + r / p.split;
+    g = p.n_full + r / p.split;
     bn = BN / p.split;
     n0 = (r % p.split) * bn;
   }
+  int m = g * CG + rank;
   Item it;
   it.tx = m % p.tiles_x; m /= p.tiles_x;
   it.ty = m % p.tiles_y; m /= p.tiles_y;
@@ -88,10 +96,13 @@ __device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int B
   return it;
 }
 
-template <int BN, int NPROD>
+// CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) runs tcgen05.mma.cta_group::2
+// with M = 256; each CTA stages its own A tile and half of the weight tile, the leader (cluster rank 0) issues.
+template <int BN, int NPROD, int CG>
 __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
-  using Cfg = UmmaCfg<BN, NPROD>;
+  using Cfg = UmmaCfg<BN, NPROD, CG>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int PLANES = Cfg::PLANES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -103,6 +114,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = p.ntaps * p.kchunks;
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // pair (or CTA) index
+  const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
@@ -113,70 +127,86 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[1]) : "memory");
     }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bars + 8 * s, 1);
-      mbar_init(bars + 64 + 8 * s, 1);
+      mbar_init(bars + 8 * s, 1);       // full: the (leader's) producer arrive.expect_tx
+      mbar_init(bars + 64 + 8 * s, 1);  // empty: one tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(bars + 128 + 8 * a, 1);  // tfull: one tcgen05.commit
-      mbar_init(bars + 144 + 8 * a, 4);  // tempty: one arrive per epilogue warp
+      mbar_init(bars + 128 + 8 * a, 1);       // tfull: one tcgen05.commit
+      mbar_init(bars + 144 + 8 * a, 4 * CG);  // tempty (leader's is used): one arrive per epilogue warp of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A tile and its share of W) =====================
     if (lane == 0) {
+      const uint32_t full0 = (CG == 2) ? mapa_rank(bars, 0) : bars;  // full barriers live in the leader
       uint32_t cnt = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const Item w = decode_item(p, item, BN);
+      for (int item = unit; item < p.n_items; item += nunits) {
+        const Item w = decode_item(p, item, BN, CG, rank);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
-        const int nbox = w.bn >> 6;
-        const uint32_t tx_bytes = (NPROD == 3 ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + w.bn * 128);
+        const int wrows = w.bn / CG;
+        const int nbox = wrows / Cfg::W_BOX;
+        const int wrow0 = w.n0 + rank * wrows;
+        const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)(A_TILE_BYTES + wrows * 128);
         for (int it = 0; it < iters; ++it, ++cnt) {
           const uint32_t s = cnt % STAGES;
           const uint32_t ph = (cnt / STAGES) & 1u;
           mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
           const int tap = it / p.kchunks, chunk = it - tap * p.kchunks;
-          const uint32_t full = bars + 8 * s;
-          mbar_expect_tx(full, tx_bytes);
+          const uint32_t full = full0 + 8 * s;
+          if ((p.dbg & 1) && cnt >= (uint32_t)STAGES) {
+            if (rank == 0) mbar_arrive(bars + 8 * s);
+            continue;
+          }
+          if (rank == 0) mbar_expect_tx(bars + 8 * s, CG * tx_bytes);
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t sw = sa + PLANES * A_TILE_BYTES;
           const int ca = p.cin_off + chunk * 64, cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
-          tma_load_4d(sa, &p.tmA[0], full, ca, cx, cy, w.img);
-          if (NPROD == 3) {
-            tma_load_4d(sa + A_TILE_BYTES, &p.tmA[1], full, ca, cx, cy, w.img);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl) {
+            if (CG == 2) tma_load_4d_pair(sa + pl * A_TILE_BYTES, &p.tmA[pl], full, ca, cx, cy, w.img);
+            else tma_load_4d(sa + pl * A_TILE_BYTES, &p.tmA[pl], full, ca, cx, cy, w.img);
             for (int b = 0; b < nbox; ++b) {
-              tma_load_3d(sa + 2 * A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
-              tma_load_3d(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES + b * 8192, &p.tmW[1], full, chunk * 64, w.n0 + 64 * b,
-                          p.slab[tap]);
+              const uint32_t dst = sw + pl * Cfg::W_TILE_BYTES + b * (Cfg::W_BOX * 128);
+              if (CG == 2) tma_load_3d_pair(dst, &p.tmW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
+              else tma_load_3d(dst, &p.tmW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
             }
-          } else {
-            for (int b = 0; b < nbox; ++b)
-              tma_load_3d(sa + A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA of the pair only) =====================
+    if (lane == 0 && rank == 0) {
       uint32_t cnt = 0, local = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
-        const Item w = decode_item(p, item, BN);
+      for (int item = unit; item < p.n_items; item += nunits, ++local) {
+        const Item w = decode_item(p, item, BN, CG, 0);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
         // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(w.bn >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc =
+            (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(w.bn >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
         const uint32_t acc = local & 1u;
-        mbar_wait(bars + 144 + 8 * acc, ((local >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait(bars + 144 + 8 * acc, ((local >> 1) & 1u) ^ 1u);  // epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem_base + acc * 256u;
         uint32_t first = 0;  // 0 for the very first MMA of the item (overwrite), 1 afterwards
@@ -188,31 +218,43 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
           const int chunk = it % p.kchunks;
           const int ksteps = (chunk == p.kchunks - 1) ? p.last_ksteps : 4;
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t sw = sa + PLANES * A_TILE_BYTES;
           const uint64_t a_hi = make_sw128_desc(sa);
+          const uint64_t w_hi = make_sw128_desc(sw);
           if (NPROD == 3) {
             const uint64_t a_lo = make_sw128_desc(sa + A_TILE_BYTES);
-            const uint64_t w_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
-            const uint64_t w_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES);
+            const uint64_t w_lo = make_sw128_desc(sw + Cfg::W_TILE_BYTES);
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t o = (uint64_t)(k * 2);  // +32 bytes (16 bf16) inside the 128-B swizzle row, >>4
-              umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+              if (CG == 2) {
+                umma_bf16_pair(d, a_hi + o, w_hi + o, idesc, first);
+                umma_bf16_pair(d, a_hi + o, w_lo + o, idesc, 1);
+                umma_bf16_pair(d, a_lo + o, w_hi + o, idesc, 1);
+              } else {
+                umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+                umma_bf16(d, a_hi + o, w_lo + o, idesc, 1);
+                umma_bf16(d, a_lo + o, w_hi + o, idesc, 1);
+              }
               first = 1;
-              umma_bf16(d, a_hi + o, w_lo + o, idesc, 1);
-              umma_bf16(d, a_lo + o, w_hi + o, idesc, 1);
             }
           } else {
-            const uint64_t w_hi = make_sw128_desc(sa + A_TILE_BYTES);
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t o = (uint64_t)(k * 2);
-              umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+              if (CG == 2) umma_bf16_pair(d, a_hi + o, w_hi + o, idesc, first);
+              else umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
               first = 1;
             }
           }
-          umma_commit(bars + 64 + 8 * s);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) umma_commit_pair(bars + 64 + 8 * s);
+          else umma_commit(bars + 64 + 8 * s);
         }
-        umma_commit(bars + 128 + 8 * acc);  // accumulator complete
+        // accumulator complete
+        if (CG == 2) umma_commit_pair(bars + 128 + 8 * acc);
+        else umma_commit(bars + 128 + 8 * acc);
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -220,9 +262,10 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     const int yy = row0 / p.TW, xx0 = row0 - yy * p.TW;
     uint8_t* slab_gen = epi_gen + q * (EPI_SLABS * 4096);
     const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
+    const uint32_t tempty0 = (CG == 2) ? mapa_rank(bars + 144, 0) : bars + 144;
     uint32_t local = 0, blk = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
-      const Item w = decode_item(p, item, BN);
+    for (int item = unit; item < p.n_items; item += nunits, ++local) {
+      const Item w = decode_item(p, item, BN, CG, rank);
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
@@ -233,8 +276,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
-        epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
-        if (strow != nullptr) {
+        if (!(p.dbg & 2))
+          epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
+        if (strow != nullptr && !(p.dbg & 4)) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -246,15 +290,23 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * acc);
+        else mbar_arrive(bars + 144 + 8 * acc);
+      }
     }
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
+    __syncwarp();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's shared memory / barriers stay valid until both CTAs are done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -264,10 +316,15 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static int g_sms = 0;
 
+static int g_dbg = 0;
+static int g_pair = 1;  // CTA-pair (cta_group::2) kernels unless AP_NETG_CTA_PAIR=0
+
 template <int BN, int NPROD>
 static int set_attr() {
-  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)UmmaCfg<BN, NPROD>::SMEM));
+  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)UmmaCfg<BN, NPROD, 1>::SMEM));
+  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)UmmaCfg<BN, NPROD, 2>::SMEM));
   return AP_OK;
 }
 
@@ -287,6 +344,10 @@ int umma_init() {
   AP_TRY((set_attr<64, 3>()));
   AP_TRY((set_attr<128, 3>()));
   AP_TRY((set_attr<256, 3>()));
+  const char* e = getenv("AP_NETG_CTA_PAIR");
+  g_pair = e ? atoi(e) : 1;  // 0: never, 1: where it wins (Cout = 256), 2: everywhere
+  const char* d = getenv("AP_UMMA_DBG");
+  g_dbg = d ? atoi(d) : 0;
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return AP_OK;
 }
@@ -319,6 +380,37 @@ int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C
   return tmap_encode(m, 1, out + ((size_t)py * Wout + px) * C, 4, dims, str, box, es);
 }
 
+// how many CTA pairs of this kernel can be resident at once (74 on a full B200; fewer if a TPC is fused off)
+template <int BN, int NPROD>
+static int max_pairs_of() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(g_sms > 0 ? g_sms : 148) & ~1u, 1, 1);
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, 2>::SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cached = n;
+  return cached;
+}
+
+static int max_pairs(int BN, int nprod) {
+  if (BN == 64) return nprod == 3 ? max_pairs_of<64, 3>() : max_pairs_of<64, 1>();
+  if (BN == 128) return nprod == 3 ? max_pairs_of<128, 3>() : max_pairs_of<128, 1>();
+  return nprod == 3 ? max_pairs_of<256, 3>() : max_pairs_of<256, 1>();
+}
+
 // `in` must be a bf16 activation. Zero-padded convs address the un-haloed interior (TMA fills
 // out-of-bounds with zeros); reflect-padded ones address the haloed buffer (halo = in.pad >= conv pad).
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
@@ -343,6 +435,11 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   UmmaParams& p = c->p;
   c->BN = g.Cout;
   c->nprod = nprod;
+  const int ntiles = (g.Wv / TW) * (g.Hv / TH) * g.B;
+  const int pairs = g_pair ? max_pairs(g.Cout, nprod) : 0;
+  // measured (profiles/r01_cta_pair.md): pairs win for N = 256 (-7..-13%), lose for N <= 128 (+9..+18%)
+  c->cg = (pairs > 0 && ntiles % 2 == 0 && (g.Cout == 256 || g_pair == 2)) ? 2 : 1;
+  const int wrows = g.Cout / c->cg;
   // activation maps
   const bool padded_view = g.reflect != 0;
   const int Hp = in.H + 2 * in.pad, Wp = in.W + 2 * in.pad;
@@ -361,7 +458,7 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
     AP_REQUIRE(g.taps.slab[i] < 9, AP_ERR_INVALID, "umma conv: only 3x3 weight slabs are packed for tcgen05");
   const uint64_t wdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
   const uint64_t wstr[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * g.Cout * 2};
-  const uint32_t wbox[3] = {64, 64, 1};
+  const uint32_t wbox[3] = {64, (uint32_t)(wrows < 64 ? wrows : 64), 1};
   const uint32_t wes[3] = {1, 1, 1};
   if (rc == AP_OK) rc = tmap_encode(&p.tmW[0], 0, w_hi, 3, wdims, wstr, wbox, wes);
   if (rc == AP_OK && nprod == 3) rc = tmap_encode(&p.tmW[1], 0, w_lo, 3, wdims, wstr, wbox, wes);
@@ -383,32 +480,48 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   p.stride = g.stride;
   p.out_coff = out_coff;
   p.stats = stats; p.stat_C = stat_C; p.stat_coff = stat_coff;
-  // item list: whole waves of full tiles, the remainder split along N so the tail fills the machine
-  const int tiles = p.tiles_x * p.tiles_y * g.B;
-  const int G = g_sms > 0 ? g_sms : 148;
-  const int rem = tiles % G;
+  // item list: whole waves of full tile groups, the remainder split along N so the tail fills the machine
+  const int groups = ntiles / c->cg;
+  const int G = c->cg == 2 ? pairs : (g_sms > 0 ? g_sms : 148);  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+  const int rem = groups % G;
   int split = 1;
   if (rem > 0) {
-    while (split < 4 && rem * split * 2 <= G && c->BN / (split * 2) >= 64) split *= 2;
+    while (split < 4 && rem * split * 2 <= G && wrows / (split * 2) >= 64) split *= 2;
   }
   p.split = split;
-  p.n_full = tiles - rem;
+  p.dbg = g_dbg;
+  p.n_full = groups - rem;
   p.n_items = p.n_full + rem * split;
-  c->grid = dim3((unsigned)(p.n_items < G ? p.n_items : G), 1);
+  c->grid = dim3((unsigned)((p.n_items < G ? p.n_items : G) * c->cg), 1);
   *out = c;
   return AP_OK;
 }
 
 void umma_conv_destroy(UmmaConv* c) { delete c; }
 
+template <int BN, int NPROD, int CG>
+static int launch_one(const UmmaConv* c, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = c->grid;
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, CG>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG == 2) ? 1 : 0;
+  AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, CG>, c->p));
+  launches_add(1);
+  return AP_OK;
+}
+
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st) {
-#define AP_UMMA_CASE(BN_, NP_)                                                                          \
-  if (c->BN == BN_ && c->nprod == NP_) {                                                                \
-    conv_umma_kernel<BN_, NP_><<<c->grid, 192, UmmaCfg<BN_, NP_>::SMEM, st>>>(c->p);                    \
-    AP_CUDA(cudaGetLastError());                                                                        \
-    launches_add(1);                                                                                    \
-    return AP_OK;                                                                                       \
-  }
+#define AP_UMMA_CASE(BN_, NP_)                                                 \
+  if (c->BN == BN_ && c->nprod == NP_)                                         \
+    return c->cg == 2 ? launch_one<BN_, NP_, 2>(c, st) : launch_one<BN_, NP_, 1>(c, st);
   AP_UMMA_CASE(64, 1)
   AP_UMMA_CASE(128, 1)
   AP_UMMA_CASE(256, 1)

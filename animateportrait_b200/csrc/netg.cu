@@ -8,6 +8,7 @@
 //   EXEC  - same walk, launching kernels on the caller's stream
 // so buffer assignment, tensor maps and launches can never disagree.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -87,7 +88,13 @@ struct Plan {
   float* h_out = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_in[3] = {nullptr, nullptr, nullptr};
+  // independent branches of the graph (encoder branches, landmark branch, ResnetBlock2 shortcuts) run on side
+  // streams so that HBM-bound kernels overlap the tensor-bound persistent convs; fork/join events by index
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> sync_ev;
   ~Plan() {
+    for (cudaStream_t s_ : side) if (s_) cudaStreamDestroy(s_);
+    for (cudaEvent_t e : sync_ev) cudaEventDestroy(e);
     for (UmmaConv* c : convs) umma_conv_destroy(c);
     if (arena) cudaFree(arena);
     if (sarena) cudaFree(sarena);
@@ -109,6 +116,7 @@ enum { CL_STEM = 0, CL_LAND = 1, CL_TRUNK = 2, CL_STRIDED = 3, CL_APPLY = 4, CL_
 struct ap_netg {
   int onc = 1, prec = 0, device = 0;
   bool profiling = false;
+  bool overlap = true;  // run independent branches on side streams (AP_NETG_OVERLAP=0 turns it off)
   std::vector<cudaEvent_t> ev;      // ev[0] = start, ev[i+1] = after launch i
   std::vector<int> ev_class;        // class of launch i
   std::vector<double> ev_flops;
@@ -149,6 +157,34 @@ struct Runner {
     if (ph == PH_EXEC && in_ready) AP_CUDA(cudaStreamWaitEvent(st, in_ready[k], 0));
     return AP_OK;
   }
+
+  // ---- branch-level concurrency: `st` is the stream the next launches go to ----
+  cudaStream_t main_st = nullptr;
+  size_t ev_i = 0;
+  bool overlap() const { return ph == PH_EXEC && !h->profiling && h->overlap; }
+  int next_event(cudaEvent_t* e) {
+    if (ev_i >= pl->sync_ev.size()) {
+      cudaEvent_t n;
+      AP_CUDA(cudaEventCreateWithFlags(&n, cudaEventDisableTiming));
+      pl->sync_ev.push_back(n);
+    }
+    *e = pl->sync_ev[ev_i++];
+    return AP_OK;
+  }
+  // everything launched on `to` from now on is ordered after what has been launched on `from` so far
+  int order_after(cudaStream_t to, cudaStream_t from) {
+    if (!overlap() || to == from) return AP_OK;
+    cudaEvent_t e;
+    AP_TRY(next_event(&e));
+    AP_CUDA(cudaEventRecord(e, from));
+    AP_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return AP_OK;
+  }
+  cudaStream_t side(int k) {
+    if (!overlap()) return main_st;
+    return pl->side[k];
+  }
+  void on(cudaStream_t s_) { st = s_; }
 
   void* alloc(size_t bytes) {
     off = align_up(off, 1024);
@@ -303,82 +339,26 @@ int Runner::run(const Inputs& in) {
   const int afmt = (prec == AP_PREC_FP32X3) ? FMT_BF16X2 : (prec == AP_PREC_BF16 ? FMT_BF16 : FMT_F32);
   const int hp = (prec == AP_PREC_FP32_SIMT) ? 0 : 1;  // halo of reflect-padded tensor-core inputs
 
+  main_st = st;
+  ev_i = 0;
   if (ph == PH_EXEC && pl->sarena_bytes) AP_CUDA(cudaMemsetAsync(pl->sarena, 0, pl->sarena_bytes, st));
+  cudaStream_t s1 = side(0), s2 = side(1), s3 = side(2);
 
-  // ---- three 7x7 stems fused into one Cout=160 problem on the photo (networks.py:1218-1243) ----
-  Raw stem = raw(B, 256, 256, 160, true);
-  AP_TRY(wait_input(0));
-  if (prec == AP_PREC_FP32_SIMT) {
-    AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
-  } else if (ph == PH_EXEC) {
-    AP_TRY(launch_stem_umma(in.input, h->w_stem_img, stem.p, stem.stats, B, prec == AP_PREC_FP32X3 ? 3 : 1, st));
-    AP_TRY(mark(CL_STEM, 2.0 * B * 65536.0 * 147 * 160));
-  }
-  tap_raw("tri00", stem, 0, 32, 1);
-  tap_raw("tri10", stem, 32, 64, 1);
-  tap_raw("tri20", stem, 96, 64, 1);
-
-  // ---- branch 1: warp L0 -> tri01 -> tri02 ----
-  Act W0 = act(B, 256, 256, 64, 0, afmt);
-  AP_TRY(wait_input(1));
-  AP_TRY(warp(stem, 0, 32, 0, in, W0, 0));
-  tap_act("warp0", W0, 0, 64);
-  Raw r01 = raw(B, 128, 128, 128, true);
-  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), W0, 0, W("model_tri01.0"), r01, 0));
-  tap_raw("tri01", r01, 0, 128, 1);
-  Act A01 = act(B, 128, 128, 128, 0, afmt);
-  AP_TRY(apply(r01, 0, 128, 1, &A01, 0, 0));
-  Raw r02 = raw(B, 64, 64, 256, true);
-  AP_TRY(conv(geom_conv(B, 128, 128, 256, 3, 2, 1, 0), A01, 0, W("model_tri02.0"), r02, 0));
-  tap_raw("tri02", r02, 0, 256, 1);
-  Act MI = act(B, 64, 64, 768, 0, afmt);  // cat[x1, x2, x3] (networks.py:1330) as channel offsets
-  AP_TRY(apply(r02, 0, 256, 1, &MI, 0, 0));
-
-  // ---- stems of branches 2 and 3, normalised once: T12 = [tri10 | tri20] ----
-  Act T12 = act(B, 256, 256, 128, 0, afmt);
-  AP_TRY(apply(stem, 32, 128, 1, &T12, 0, 0));
-
-  // ---- branch 2: tri11 -> warp L1 -> tri12 ----
-  Raw r11 = raw(B, 128, 128, 64, true);
-  AP_TRY(conv(geom_conv(B, 256, 64, 64, 3, 2, 1, 0), T12, 0, W("model_tri11.0"), r11, 0));
-  tap_raw("tri11", r11, 0, 64, 1);
-  Act W1 = act(B, 128, 128, 128, 0, afmt);
-  AP_TRY(warp(r11, 0, 64, 1, in, W1, 0));
-  tap_act("warp1", W1, 0, 128);
-  Raw r12 = raw(B, 64, 64, 256, true);
-  AP_TRY(conv(geom_conv(B, 128, 128, 256, 3, 2, 1, 0), W1, 0, W("model_tri12.0"), r12, 0));
-  tap_raw("tri12", r12, 0, 256, 1);
-  AP_TRY(apply(r12, 0, 256, 1, &MI, 256, 0));
-
-  // ---- branch 3: tri21 -> tri22 -> warp L2 ----
-  Raw r21 = raw(B, 128, 128, 128, true);
-  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), T12, 64, W("model_tri21.0"), r21, 0));
-  tap_raw("tri21", r21, 0, 128, 1);
-  Act A21 = act(B, 128, 128, 128, 0, afmt);
-  AP_TRY(apply(r21, 0, 128, 1, &A21, 0, 0));
-  Raw r22 = raw(B, 64, 64, 128, true);
-  AP_TRY(conv(geom_conv(B, 128, 128, 128, 3, 2, 1, 0), A21, 0, W("model_tri22.0"), r22, 0));
-  tap_raw("tri22", r22, 0, 128, 1);
-  AP_TRY(warp(r22, 0, 128, 2, in, MI, 512));
-  tap_act("warp2", MI, 512, 256);
-
-  // ---- merge: Conv3 768->256, zero pad, bias kept, no norm (networks.py:1251,1330) ----
-  Raw rM = raw(B, 64, 64, 256, false);
-  AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0));
+  // trunk buffers (the landmark branch writes its 2 x 16 channels of XL early, on a side stream)
   Act XL = act(B, 64, 64, 288, hp, afmt);  // cat[x, l1, l2] (networks.py:1335)
   Act X = act(B, 64, 64, 256, hp, afmt);
   Act T = act(B, 64, 64, 256, hp, afmt);
   Act D0 = act(B, 64, 64, 256, 0, afmt);   // decoder input
   float* xres[10];
   for (int i = 0; i < 10; ++i) xres[i] = (float*)alloc((size_t)B * 64 * 64 * 256 * sizeof(float));
-  AP_TRY(apply(rM, 0, 256, 0, &XL, 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
-  tap_f32("merge", xres[0], B, 64, 64, 256);
 
   // ---- landmark branch on land1 and land2 as one batch of 2B maps (networks.py:1280-1282, 1331-1332) ----
   {
     Raw rl0 = raw(2 * B, 256, 256, 8, true);
     Raw rl1 = raw(2 * B, 128, 128, 16, true);
     Raw rl2 = raw(2 * B, 64, 64, 16, true);
+    AP_TRY(order_after(s3, main_st));
+    on(s3);
     AP_TRY(wait_input(2));
     if (ph == PH_EXEC) {
       AP_TRY(launch_landmark_branch(in.land1, in.land2, W("model_landmark_trans.0").host.data(),
@@ -396,7 +376,83 @@ int Runner::run(const Inputs& in) {
       AP_TRY(apply(v, 0, 16, 0, &XL, 256 + 16 * li, 1));
       tap_act(li == 0 ? "land1" : "land2", XL, 256 + 16 * li, 16);
     }
+    on(main_st);
   }
+
+  // ---- three 7x7 stems fused into one Cout=160 problem on the photo (networks.py:1218-1243) ----
+  Raw stem = raw(B, 256, 256, 160, true);
+  AP_TRY(wait_input(0));
+  if (prec == AP_PREC_FP32_SIMT) {
+    AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
+  } else if (ph == PH_EXEC) {
+    AP_TRY(launch_stem_umma(in.input, h->w_stem_img, stem.p, stem.stats, B, prec == AP_PREC_FP32X3 ? 3 : 1, st));
+    AP_TRY(mark(CL_STEM, 2.0 * B * 65536.0 * 147 * 160));
+  }
+  tap_raw("tri00", stem, 0, 32, 1);
+  tap_raw("tri10", stem, 32, 64, 1);
+  tap_raw("tri20", stem, 96, 64, 1);
+
+  AP_TRY(order_after(s1, main_st));
+
+  // ---- branch 1 (main stream): warp L0 -> tri01 -> tri02 ----
+  Act W0 = act(B, 256, 256, 64, 0, afmt);
+  AP_TRY(wait_input(1));
+  AP_TRY(warp(stem, 0, 32, 0, in, W0, 0));
+  tap_act("warp0", W0, 0, 64);
+  Raw r01 = raw(B, 128, 128, 128, true);
+  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), W0, 0, W("model_tri01.0"), r01, 0));
+  tap_raw("tri01", r01, 0, 128, 1);
+  Act A01 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(apply(r01, 0, 128, 1, &A01, 0, 0));
+  Raw r02 = raw(B, 64, 64, 256, true);
+  AP_TRY(conv(geom_conv(B, 128, 128, 256, 3, 2, 1, 0), A01, 0, W("model_tri02.0"), r02, 0));
+  tap_raw("tri02", r02, 0, 256, 1);
+  Act MI = act(B, 64, 64, 768, 0, afmt);  // cat[x1, x2, x3] (networks.py:1330) as channel offsets
+  AP_TRY(apply(r02, 0, 256, 1, &MI, 0, 0));
+
+  // ---- stems of branches 2 and 3, normalised once: T12 = [tri10 | tri20] (side stream 1) ----
+  on(s1);
+  Act T12 = act(B, 256, 256, 128, 0, afmt);
+  AP_TRY(apply(stem, 32, 128, 1, &T12, 0, 0));
+  AP_TRY(order_after(s2, s1));
+
+  // ---- branch 2 (side stream 1): tri11 -> warp L1 -> tri12 ----
+  Raw r11 = raw(B, 128, 128, 64, true);
+  AP_TRY(conv(geom_conv(B, 256, 64, 64, 3, 2, 1, 0), T12, 0, W("model_tri11.0"), r11, 0));
+  tap_raw("tri11", r11, 0, 64, 1);
+  Act W1 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(wait_input(1));
+  AP_TRY(warp(r11, 0, 64, 1, in, W1, 0));
+  tap_act("warp1", W1, 0, 128);
+  Raw r12 = raw(B, 64, 64, 256, true);
+  AP_TRY(conv(geom_conv(B, 128, 128, 256, 3, 2, 1, 0), W1, 0, W("model_tri12.0"), r12, 0));
+  tap_raw("tri12", r12, 0, 256, 1);
+  AP_TRY(apply(r12, 0, 256, 1, &MI, 256, 0));
+
+  // ---- branch 3 (side stream 2): tri21 -> tri22 -> warp L2 ----
+  on(s2);
+  Raw r21 = raw(B, 128, 128, 128, true);
+  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), T12, 64, W("model_tri21.0"), r21, 0));
+  tap_raw("tri21", r21, 0, 128, 1);
+  Act A21 = act(B, 128, 128, 128, 0, afmt);
+  AP_TRY(apply(r21, 0, 128, 1, &A21, 0, 0));
+  Raw r22 = raw(B, 64, 64, 128, true);
+  AP_TRY(conv(geom_conv(B, 128, 128, 128, 3, 2, 1, 0), A21, 0, W("model_tri22.0"), r22, 0));
+  tap_raw("tri22", r22, 0, 128, 1);
+  AP_TRY(wait_input(1));
+  AP_TRY(warp(r22, 0, 128, 2, in, MI, 512));
+  tap_act("warp2", MI, 512, 256);
+  on(main_st);
+  AP_TRY(order_after(main_st, s1));
+  AP_TRY(order_after(main_st, s2));
+
+  // ---- merge: Conv3 768->256, zero pad, bias kept, no norm (networks.py:1251,1330) ----
+  Raw rM = raw(B, 64, 64, 256, false);
+  AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0));
+  AP_TRY(apply(rM, 0, 256, 0, &XL, 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
+  tap_f32("merge", xres[0], B, 64, 64, 256);
+
+  AP_TRY(order_after(main_st, s3));
 
   // ---- 9 residual blocks (networks.py:1333-1337, 2303-2421) ----
   for (int i = 0; i < 9; ++i) {
@@ -407,15 +463,21 @@ int Runner::run(const Inputs& in) {
     const Act* dst = (i == 8) ? &D0 : (((i + 1) % 3 == 0) ? &XL : &X);
     const int dst_halo = (i == 8) ? 0 : 1;
     Raw rs;
-    if (b2) {
-      rs = raw(B, 64, 64, 256, true);
-      AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0));
-    }
     Raw r1 = raw(B, 64, 64, 256, true);
     AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 1), src, 0, W(b + ".conv_block.1"), r1, 0));
+    if (b2) {
+      // the shortcut conv only depends on the block input: it runs on a side stream, under it the
+      // HBM-bound InstanceNorm apply of conv_block.1
+      rs = raw(B, 64, 64, 256, true);
+      AP_TRY(order_after(s1, main_st));
+      on(s1);
+      AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0));
+      on(main_st);
+    }
     AP_TRY(apply(r1, 0, 256, 1, &T, 0, 1));
     Raw r2 = raw(B, 64, 64, 256, true);
     AP_TRY(conv(geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, 0, W(b + ".conv_block.5"), r2, 0));
+    if (b2) AP_TRY(order_after(main_st, s1));
     if (b2) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1]));
     else AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, xres[i], xres[i + 1]));
     const std::string tn = "block" + std::to_string(i);
@@ -464,6 +526,12 @@ static int get_plan(ap_netg* h, int B, Plan** out) {
   Runner rb{h, pl, PH_BUILD, nullptr};
   rc = rb.run(none);
   if (rc != AP_OK) { delete pl; return rc; }
+  for (cudaStream_t& s_ : pl->side)
+    if (cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("side stream creation failed");
+      delete pl;
+      return AP_ERR_CUDA;
+    }
   h->plans[B] = pl;
   *out = pl;
   return AP_OK;
@@ -494,6 +562,8 @@ int ap_netg_create(ap_netg** handle, int output_nc, int precision, int device) {
   if (precision != AP_PREC_FP32_SIMT) AP_TRY(umma_init());
   ap_netg* h = new ap_netg();
   h->onc = output_nc; h->prec = precision; h->device = device;
+  const char* ov = getenv("AP_NETG_OVERLAP");
+  h->overlap = !(ov && ov[0] == '0');
   *handle = h;
   return AP_OK;
 }

@@ -185,3 +185,22 @@ def test_weights_can_be_swapped_and_errors_surface(dev):
 def test_native_library_is_the_loaded_code_path(dev):
     maps = open("/proc/self/maps").read()
     assert "libapnetg.so" in maps
+
+
+def test_branch_overlap_on_side_streams_matches_serial_execution(dev, monkeypatch):
+    """Independent branches (encoder branches, landmark branch, ResnetBlock2 shortcuts) run on side streams;
+    AP_NETG_OVERLAP=0 serialises them on the caller's stream.  Same kernels, same result."""
+    sd = O.make_state_dict(1, seed=5, bias_std=0.2)
+    inputs = [t.to(dev) for t in O.make_inputs(3, seed=77, kind="noise")]
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AP_NETG_OVERLAP", mode)
+        net = _net(1, sd, dev, "fp32").module
+        with torch.no_grad():
+            ys = [net(*inputs).clone() for _ in range(3)]  # repeated: workspace reuse across forwards stays ordered
+        torch.cuda.synchronize()
+        assert all((y - ys[0]).abs().max().item() <= 2e-4 for y in ys)
+        outs[mode] = ys[-1]
+    assert (outs["1"] - outs["0"]).abs().max().item() <= 2e-4
+    y_ref = O.netg_forward(sd, *[t[1:2].cpu() for t in inputs])
+    assert (outs["1"][1:2].cpu() - y_ref).abs().max().item() <= FP32_TOL

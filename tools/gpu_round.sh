@@ -34,8 +34,18 @@ if has list; then
   echo "ncu list rc=$?"
 fi
 if has full; then
-  timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 300 --launch-count 80 \
-    -o $OUT/${TAG}_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_full.log 2>&1
+  # one whole forward (71 launches) with the full metric set; the .ncu-rep is reduced to CSV on the box because
+  # gpurun only brings back 64 MiB
+  timeout 1200 ncu --set full --clock-control none --launch-skip 300 --launch-count 71 \
+    -o /tmp/${TAG}_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_full.log 2>&1
   echo "ncu full rc=$?"
-  ls -la $OUT
+  ncu -i /tmp/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
+  python tools/ncu_summary.py /tmp/${TAG}_full.ncu-rep > $OUT/${TAG}_full_summary.txt 2>&1
 fi
+if has src; then
+  # source-level capture of the dominant kernel only (3 launches), small enough to travel
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-conv_umma} --launch-skip ${NCU_SKIP:-40} --launch-count 3 \
+    -o $OUT/${TAG}_src -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_src.log 2>&1
+  echo "ncu src rc=$?"
+fi
+ls -la $OUT
