@@ -6,7 +6,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libapnetg.so")
+# AP_NETG_LIB selects another BUILD of the same library (A/B timing of kernel variants); there is still no fallback
+LIB_PATH = os.environ.get("AP_NETG_LIB") or os.path.join(_PKG, "lib", "libapnetg.so")
 
 AP_PREC_FP32X3 = 0
 AP_PREC_BF16 = 1

@@ -31,6 +31,13 @@ namespace ap {
 
 void launches_add(int n);
 
+// timing diagnostics are compiled in only with -DAP_UMMA_DIAG (tools/conv_probe.sh builds such a library)
+#ifdef AP_UMMA_DIAG
+#define AP_DBG(x) (x)
+#else
+#define AP_DBG(x) 0
+#endif
+
 struct alignas(64) UmmaParams {
   CUtensorMap tmA[2];  // hi, lo
   CUtensorMap tmW[2];
@@ -76,6 +83,198 @@ struct Item {
   int img, ty, tx, n0, bn;
 };
 
+// ---- single-CTA kernel (cta_group::1): one CTA per 128-pixel tile; used for the N <= 128 layers ----
+__device__ __forceinline__ Item decode_item1(const UmmaParams& p, int item, int BN) {
+  int m, n0 = 0, bn = BN;
+  if (item < p.n_full) {
+    m = item;
+  } else {
+    const int r = item - p.n_full;
+    m = p.n_full + r / p.split;
+    bn = BN / p.split;
+    n0 = (r % p.split) * bn;
+  }
+  Item it;
+  it.tx = m % p.tiles_x; m /= p.tiles_x;
+  it.ty = m % p.tiles_y; m /= p.tiles_y;
+  it.img = m;
+  it.n0 = n0;
+  it.bn = bn;
+  return it;
+}
+
+template <int BN, int NPROD>
+__global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constant__ UmmaParams p) {
+  using Cfg = UmmaCfg<BN, NPROD, 1>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t epi_s = smem_base + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bars = epi_s + EPI_BYTES;
+  // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int iters = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO) : "memory");
+    if (NPROD == 3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[1]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[1]) : "memory");
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 64 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bars + 128 + 8 * a, 1);  // tfull: one tcgen05.commit
+      mbar_init(bars + 144 + 8 * a, 4);  // tempty: one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item w = decode_item1(p, item, BN);
+        const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
+        const int nbox = w.bn >> 6;
+        const uint32_t tx_bytes = (NPROD == 3 ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + w.bn * 128);
+        for (int it = 0; it < iters; ++it, ++cnt) {
+          const uint32_t s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1u;
+          mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
+          const int tap = it / p.kchunks, chunk = it - tap * p.kchunks;
+          const uint32_t full = bars + 8 * s;
+          mbar_expect_tx(full, tx_bytes);
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const int ca = p.cin_off + chunk * 64, cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
+          tma_load_4d(sa, &p.tmA[0], full, ca, cx, cy, w.img);
+          if (NPROD == 3) {
+            tma_load_4d(sa + A_TILE_BYTES, &p.tmA[1], full, ca, cx, cy, w.img);
+            for (int b = 0; b < nbox; ++b) {
+              tma_load_3d(sa + 2 * A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
+              tma_load_3d(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES + b * 8192, &p.tmW[1], full, chunk * 64, w.n0 + 64 * b,
+                          p.slab[tap]);
+            }
+          } else {
+            for (int b = 0; b < nbox; ++b)
+              tma_load_3d(sa + A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0, local = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+        const Item w = decode_item1(p, item, BN);
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+        // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(w.bn >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t acc = local & 1u;
+        mbar_wait(bars + 144 + 8 * acc, ((local >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 256u;
+        uint32_t first = 0;  // 0 for the very first MMA of the item (overwrite), 1 afterwards
+        for (int it = 0; it < iters; ++it, ++cnt) {
+          const uint32_t s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1u;
+          mbar_wait(bars + 8 * s, ph);
+          tc_fence_after();
+          const int chunk = it % p.kchunks;
+          const int ksteps = (chunk == p.kchunks - 1) ? p.last_ksteps : 4;
+          const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
+          const uint64_t a_hi = make_sw128_desc(sa);
+          if (NPROD == 3) {
+            const uint64_t a_lo = make_sw128_desc(sa + A_TILE_BYTES);
+            const uint64_t w_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
+            const uint64_t w_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);  // +32 bytes (16 bf16) inside the 128-B swizzle row, >>4
+              umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+              first = 1;
+              umma_bf16(d, a_hi + o, w_lo + o, idesc, 1);
+              umma_bf16(d, a_lo + o, w_hi + o, idesc, 1);
+            }
+          } else {
+            const uint64_t w_hi = make_sw128_desc(sa + A_TILE_BYTES);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              umma_bf16(d, a_hi + o, w_hi + o, idesc, first);
+              first = 1;
+            }
+          }
+          umma_commit(bars + 64 + 8 * s);  // frees the smem stage when these MMAs retire
+        }
+        umma_commit(bars + 128 + 8 * acc);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row0 = q * 32;
+    const int yy = row0 / p.TW, xx0 = row0 - yy * p.TW;
+    uint8_t* slab_gen = epi_gen + q * (EPI_SLABS * 4096);
+    const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
+    uint32_t local = 0, blk = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      const Item w = decode_item1(p, item, BN);
+      const uint32_t acc = local & 1u;
+      mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
+      tc_fence_after();
+      const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
+      double* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + w.n0 + lane) * 2 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
+        const uint32_t sl = (blk % EPI_SLABS) * 4096;
+        epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
+        if (strow != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float cs = butterfly_colsum(v, lane);
+          const float cq = butterfly_colsum(sq, lane);
+          atomicAdd(strow + (size_t)c0 * 2, (double)cs);
+          atomicAdd(strow + (size_t)c0 * 2 + 1, (double)cq);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
+    }
+    if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
+// ---- CTA-pair capable kernel ----
 __device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int BN, int CG, int rank) {
   int g, n0 = 0, bn = BN;
   if (item < p.n_full) {
@@ -173,7 +372,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
           mbar_wait(bars + 64 + 8 * s, ph ^ 1u);
           const int tap = it / p.kchunks, chunk = it - tap * p.kchunks;
           const uint32_t full = full0 + 8 * s;
-          if ((p.dbg & 1) && cnt >= (uint32_t)STAGES) {
+          if (AP_DBG(p.dbg & 1) && cnt >= (uint32_t)STAGES) {
             if (rank == 0) mbar_arrive(bars + 8 * s);
             continue;
           }
@@ -181,11 +380,17 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
           const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t sw = sa + PLANES * A_TILE_BYTES;
           const int ca = p.cin_off + chunk * 64, cx = x0 + p.dx[tap], cy = y0 + p.dy[tap];
+          // issue order: both A planes first, then the W boxes with hi/lo interleaved.  The order matters: identical
+          // W requests of different SMs that reach L2 close together are served once (measured: planes-outer order
+          // is 12-20 % slower on the L2-fabric-bound layers)
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl) {
             if (CG == 2) tma_load_4d_pair(sa + pl * A_TILE_BYTES, &p.tmA[pl], full, ca, cx, cy, w.img);
             else tma_load_4d(sa + pl * A_TILE_BYTES, &p.tmA[pl], full, ca, cx, cy, w.img);
-            for (int b = 0; b < nbox; ++b) {
+          }
+          for (int b = 0; b < nbox; ++b) {
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl) {
               const uint32_t dst = sw + pl * Cfg::W_TILE_BYTES + b * (Cfg::W_BOX * 128);
               if (CG == 2) tma_load_3d_pair(dst, &p.tmW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
               else tma_load_3d(dst, &p.tmW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
@@ -276,9 +481,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
-        if (!(p.dbg & 2))
+        if (!AP_DBG(p.dbg & 2))
           epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
-        if (strow != nullptr && !(p.dbg & 4)) {
+        if (strow != nullptr && !AP_DBG(p.dbg & 4)) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -321,7 +526,7 @@ static int g_pair = 1;  // CTA-pair (cta_group::2) kernels unless AP_NETG_CTA_PA
 
 template <int BN, int NPROD>
 static int set_attr() {
-  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AP_CUDA(cudaFuncSetAttribute(conv_umma1_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)UmmaCfg<BN, NPROD, 1>::SMEM));
   AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)UmmaCfg<BN, NPROD, 2>::SMEM));
@@ -437,8 +642,9 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   c->nprod = nprod;
   const int ntiles = (g.Wv / TW) * (g.Hv / TH) * g.B;
   const int pairs = g_pair ? max_pairs(g.Cout, nprod) : 0;
-  // measured (profiles/r01_cta_pair.md): pairs win for N = 256 (-7..-13%), lose for N <= 128 (+9..+18%)
-  c->cg = (pairs > 0 && ntiles % 2 == 0 && (g.Cout == 256 || g_pair == 2)) ? 2 : 1;
+  // measured (profiles/r01_cta_pair.md): pairs win for N = 256 with the 3-product operands (-7..-13%), lose for
+  // N <= 128 (+9..+18%) and for single-product bf16 (+8%: 512-cycle stages are too short for the pair handshake)
+  c->cg = (pairs > 0 && ntiles % 2 == 0 && ((g.Cout == 256 && nprod == 3) || g_pair == 2)) ? 2 : 1;
   const int wrows = g.Cout / c->cg;
   // activation maps
   const bool padded_view = g.reflect != 0;
@@ -501,19 +707,24 @@ void umma_conv_destroy(UmmaConv* c) { delete c; }
 
 template <int BN, int NPROD, int CG>
 static int launch_one(const UmmaConv* c, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = c->grid;
-  cfg.blockDim = dim3(192, 1, 1);
-  cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, CG>::SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = (CG == 2) ? 1 : 0;
-  AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, CG>, c->p));
+  if constexpr (CG == 1) {
+    conv_umma1_kernel<BN, NPROD><<<c->grid, 192, UmmaCfg<BN, NPROD, 1>::SMEM, st>>>(c->p);
+    AP_CUDA(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = c->grid;
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, 2>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2>, c->p));
+  }
   launches_add(1);
   return AP_OK;
 }
