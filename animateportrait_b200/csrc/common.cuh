@@ -134,6 +134,21 @@ struct ReadP {  // debug tap: Act or Raw(+stats) -> NCHW fp32
   float* dst;
 };
 
+// (mean, rstd) of an affine-less InstanceNorm2d from the producer's {sum, sum of squares} (fp64), eps = 1e-5
+// (nn.InstanceNorm2d default, Module2/models/networks.py:34): biased variance over the H*W plane.
+#ifdef __CUDACC__
+__device__ __forceinline__ void stats_to_affine(const double* st, int n, int stat_C, int stat_coff, int c, double inv_n,
+                                                float* mean, float* rstd) {
+  const double su = st[((size_t)n * stat_C + stat_coff + c) * 2 + 0];
+  const double sq = st[((size_t)n * stat_C + stat_coff + c) * 2 + 1];
+  const double m = su * inv_n;
+  double var = sq * inv_n - m * m;  // sums are exact enough in double; the reference's own IN is fp32
+  if (var < 0.0) var = 0.0;
+  *mean = (float)m;
+  *rstd = 1.0f / sqrtf((float)var + 1e-5f);
+}
+#endif
+
 // ---- launchers (each returns AP_OK / error and counts one launch) ----
 int launch_conv_simt(const SimtConvP& p, cudaStream_t st);
 int launch_apply(const ApplyP& p, cudaStream_t st);
@@ -166,6 +181,11 @@ int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C
 size_t stem_umma_weight_bytes();
 int launch_pack_stem_umma(const float* src, int cout_s, int coff, uint8_t* img, cudaStream_t st);
 int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* stats, int B, int nprod, cudaStream_t st);
+
+// ---- tcgen05 output stage (conv_out.cu): IN+ReLU -> RefPad3 -> Conv7x7 64->onc -> bias -> tanh ----
+size_t out_umma_weight_bytes(int onc);
+int launch_pack_out_umma(const float* src, int onc, uint8_t* img, cudaStream_t st);
+int launch_out_umma(const OutConvP& p, const uint8_t* wimg, cudaStream_t st);
 
 // ---- landmark branch (landmark.cu): three direct convs over both landmark maps ----
 int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,

@@ -64,8 +64,14 @@ struct UmmaConv {
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
-constexpr int EPI_SLABS = 2;             // staging slabs per epilogue warp
-constexpr int EPI_BYTES = 4 * EPI_SLABS * 4096;
+// Epilogue staging slabs (4 KB) per epilogue warp.  The N <= 128 kernels keep one: that leaves ~17 KB of the SM's
+// shared memory unallocated, enough for CTAs of the HBM-bound kernels (warps, applies) of the other encoder
+// branches to be co-resident with a persistent conv CTA -- without it the side streams cannot overlap anything.
+template <int BN>
+struct EpiCfg {
+  static constexpr int SLABS = BN >= 256 ? 2 : 1;
+  static constexpr int BYTES = 4 * SLABS * 4096;
+};
 
 template <int BN, int NPROD, int CG>
 struct UmmaCfg {
@@ -74,7 +80,8 @@ struct UmmaCfg {
   static constexpr int W_BOX = W_ROWS < 64 ? W_ROWS : 64;    // rows per TMA box
   static constexpr int W_TILE_BYTES = W_ROWS * 128;
   static constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + W_TILE_BYTES);
-  static constexpr int STAGES_RAW = (226 * 1024 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
+  static constexpr int STAGES_RAW = (226 * 1024 - 2 * 4 * 4096 - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
@@ -112,6 +119,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_s = smem_base + STAGES * Cfg::STAGE_BYTES;
   uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
+  constexpr int EPI_SLABS = EpiCfg<BN>::SLABS;
+  constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
   const uint32_t bars = epi_s + EPI_BYTES;
   // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);
@@ -307,6 +316,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_s = smem_base + STAGES * Cfg::STAGE_BYTES;
   uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
+  constexpr int EPI_SLABS = EpiCfg<BN>::SLABS;
+  constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
   const uint32_t bars = epi_s + EPI_BYTES;
   // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);

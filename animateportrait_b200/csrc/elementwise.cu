@@ -53,17 +53,6 @@ __device__ __forceinline__ void store_pixel(const Dst& d, int n, int y, int x, i
   }
 }
 
-__device__ __forceinline__ void stats_to_affine(const double* st, int n, int stat_C, int stat_coff, int c,
-                                                double inv_n, float* mean, float* rstd) {
-  const double su = st[((size_t)n * stat_C + stat_coff + c) * 2 + 0];
-  const double sq = st[((size_t)n * stat_C + stat_coff + c) * 2 + 1];
-  const double m = su * inv_n;
-  double var = sq * inv_n - m * m;  // sums are exact enough in double; the reference's own IN is fp32
-  if (var < 0.0) var = 0.0;
-  *mean = (float)m;
-  *rstd = 1.0f / sqrtf((float)var + 1e-5f);  // eps of nn.InstanceNorm2d (networks.py:34)
-}
-
 // ------------------------------------------------------------------------------------------------
 // apply: y = IN(raw) [+ IN(raw2)] [+ bias] [+ res_in], optional ReLU; -> res_out (fp32) and/or dst.
 // grid (pixel chunks, B).  TPP = C/4 threads per pixel: a thread keeps ONE channel quad (its mean / rstd
@@ -77,10 +66,13 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
   return r;
 }
 
-template <int TPP>
-__global__ void __launch_bounds__(256) apply_kernel(const ApplyP p) {
+// MODE 0: IN (or bias) [+ReLU];  1: + InstanceNorm'ed second operand (ResnetBlock2 shortcut);  2: + fp32 residual.
+// 85 registers at most (3 CTAs = 24 warps per SM, each thread with 4-12 independent 16-byte loads in flight) and
+// CTAs of only 8 pixel passes, so that the grid is several balanced waves instead of 1.7 fat ones.
+template <int TPP, int MODE>
+__global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   constexpr int NY = 256 / TPP;  // pixels per pass
-  constexpr int APPLY_PIX_PER_CTA = (4 * NY > 128) ? 4 * NY : 128;
+  constexpr int APPLY_PIX_PER_CTA = 8 * NY;
   const int n = blockIdx.y;
   const int cq = threadIdx.x % TPP, py = threadIdx.x / TPP;
   const int c = cq * 4;
@@ -93,24 +85,24 @@ __global__ void __launch_bounds__(256) apply_kernel(const ApplyP p) {
     for (int e = 0; e < 4; ++e) {
       if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
       else { mean[e] = p.bias ? -p.bias[c + e] : 0.f; rstd[e] = 1.f; }
-      if (p.raw2) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
+      if (MODE == 1) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
     }
   }
   Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
   const int pix0 = blockIdx.x * APPLY_PIX_PER_CTA + py;
   const float* raw = p.raw + ((size_t)n * HW) * p.raw_C + p.raw_coff + c;
-  const float* raw2 = p.raw2 ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
-  const float* rin = p.res_in ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
+  const float* raw2 = (MODE == 1) ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
+  const float* rin = (MODE == 2) ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
   float* rout = p.res_out ? p.res_out + ((size_t)n * HW) * p.C + c : nullptr;
 #pragma unroll 1
   for (int k0 = 0; k0 < APPLY_PIX_PER_CTA; k0 += 4 * NY) {
-    float4 v[4], u[4], r[4];
+    float4 v[4], u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int pix = pix0 + k0 + j * NY;
       v[j] = ld_stream(raw + (size_t)pix * p.raw_C);
-      if (raw2) u[j] = ld_stream(raw2 + (size_t)pix * p.raw2_C);
-      if (rin) r[j] = ld_stream(rin + (size_t)pix * p.C);
+      if (MODE == 1) u[j] = ld_stream(raw2 + (size_t)pix * p.raw2_C);
+      if (MODE == 2) u[j] = ld_stream(rin + (size_t)pix * p.C);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -121,29 +113,37 @@ __global__ void __launch_bounds__(256) apply_kernel(const ApplyP p) {
       o.z = (v[j].z - mean[2]) * rstd[2];
       o.w = (v[j].w - mean[3]) * rstd[3];
       if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      if (raw2) {
+      if (MODE == 1) {
         o.x += (u[j].x - mean2[0]) * rstd2[0];
         o.y += (u[j].y - mean2[1]) * rstd2[1];
         o.z += (u[j].z - mean2[2]) * rstd2[2];
         o.w += (u[j].w - mean2[3]) * rstd2[3];
       }
-      if (rin) { o.x += r[j].x; o.y += r[j].y; o.z += r[j].z; o.w += r[j].w; }
+      if (MODE == 2) { o.x += u[j].x; o.y += u[j].y; o.z += u[j].z; o.w += u[j].w; }
       if (rout) *reinterpret_cast<float4*>(rout + (size_t)pix * p.C) = o;
       if (p.fmt >= 0) store_pixel(d, n, pix >> logW, pix & (p.W - 1), c, o);
     }
   }
 }
 
+template <int TPP>
+static void launch_apply_tpp(const ApplyP& p, dim3 grid, cudaStream_t st) {
+  if (p.raw2) apply_kernel<TPP, 1><<<grid, 256, 0, st>>>(p);
+  else if (p.res_in) apply_kernel<TPP, 2><<<grid, 256, 0, st>>>(p);
+  else apply_kernel<TPP, 0><<<grid, 256, 0, st>>>(p);
+}
+
 int launch_apply(const ApplyP& p, cudaStream_t st) {
   AP_REQUIRE(p.C == 16 || p.C == 128 || p.C == 256, AP_ERR_INVALID, "apply: C=%d (16, 128 or 256)", p.C);
   AP_REQUIRE(p.raw_C % 4 == 0 && p.raw_coff % 4 == 0, AP_ERR_INVALID, "apply: raw channel layout not 16B aligned");
   AP_REQUIRE(p.fmt < 0 || (p.dC % 4 == 0 && p.dcoff % 4 == 0), AP_ERR_INVALID, "apply: dst channel layout");
-  const int ppc = (p.C == 16) ? 256 : 128;  // pixels per CTA (matches APPLY_PIX_PER_CTA in the kernel)
+  AP_REQUIRE(!(p.raw2 && p.res_in), AP_ERR_INVALID, "apply: shortcut operand and residual stream are exclusive");
+  const int ppc = 8 * (256 / (p.C / 4));  // pixels per CTA (matches APPLY_PIX_PER_CTA in the kernel)
   AP_REQUIRE((p.W & (p.W - 1)) == 0 && (p.H * p.W) % ppc == 0, AP_ERR_INVALID, "apply: %dx%d", p.H, p.W);
   dim3 grid(p.H * p.W / ppc, p.B);
-  if (p.C == 256) apply_kernel<64><<<grid, 256, 0, st>>>(p);
-  else if (p.C == 128) apply_kernel<32><<<grid, 256, 0, st>>>(p);
-  else apply_kernel<4><<<grid, 256, 0, st>>>(p);
+  if (p.C == 256) launch_apply_tpp<64>(p, grid, st);
+  else if (p.C == 128) launch_apply_tpp<32>(p, grid, st);
+  else launch_apply_tpp<4>(p, grid, st);
   AP_CUDA(cudaGetLastError());
   launches_add(1);
   return AP_OK;

@@ -117,6 +117,7 @@ struct ap_netg {
   int onc = 1, prec = 0, device = 0;
   bool profiling = false;
   bool overlap = true;  // run independent branches on side streams (AP_NETG_OVERLAP=0 turns it off)
+  bool out_umma = true; // tcgen05 output stage (AP_NETG_OUT_UMMA=0: CUDA-core kernel)
   std::vector<cudaEvent_t> ev;      // ev[0] = start, ev[i+1] = after launch i
   std::vector<int> ev_class;        // class of launch i
   std::vector<double> ev_flops;
@@ -126,6 +127,7 @@ struct ap_netg {
   float* w_stem = nullptr;   // fused stems [49][3][160] (CUDA-core path)
   uint8_t* w_stem_img = nullptr;  // fused stems, pre-swizzled bf16 hi/lo smem image (tcgen05 path)
   float* w_out = nullptr;    // [onc][49][64]
+  uint8_t* w_out_img = nullptr;  // tcgen05 output stage: pre-swizzled bf16 hi/lo images per output channel
   float* b_merge = nullptr;  // [256]
   float* b_out = nullptr;    // [onc]
   std::vector<void*> owned;  // every device allocation holding weights
@@ -498,7 +500,8 @@ int Runner::run(const Inputs& in) {
   if (ph == PH_EXEC) {
     OutConvP p{};
     p.raw = ru1.p; p.stats = ru1.stats; p.w = h->w_out; p.bias = h->b_out; p.out = in.out; p.B = B; p.onc = h->onc;
-    AP_TRY(launch_out_conv(p, st));
+    if (h->w_out_img && h->out_umma) AP_TRY(launch_out_umma(p, h->w_out_img, st));
+    else AP_TRY(launch_out_conv(p, st));
     AP_TRY(mark(CL_OUT, 2.0 * B * 256.0 * 256.0 * 64 * 49 * h->onc));
   }
   return AP_OK;
@@ -564,6 +567,8 @@ int ap_netg_create(ap_netg** handle, int output_nc, int precision, int device) {
   h->onc = output_nc; h->prec = precision; h->device = device;
   const char* ov = getenv("AP_NETG_OVERLAP");
   h->overlap = !(ov && ov[0] == '0');
+  const char* ou = getenv("AP_NETG_OUT_UMMA");
+  h->out_umma = !(ou && ou[0] == '0');
   *handle = h;
   return AP_OK;
 }
@@ -574,6 +579,7 @@ static void free_weights(ap_netg* h) {
   h->w.clear();
   h->w_stem = h->w_out = h->b_merge = h->b_out = nullptr;
   h->w_stem_img = nullptr;
+  h->w_out_img = nullptr;
   h->loaded = false;
 }
 
@@ -627,6 +633,7 @@ int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const floa
   AP_TRY(dalloc((size_t)49 * 3 * 160 * 4, (void**)&h->w_stem));
   if (h->prec != AP_PREC_FP32_SIMT) AP_TRY(dalloc(stem_umma_weight_bytes(), (void**)&h->w_stem_img));
   AP_TRY(dalloc((size_t)h->onc * 49 * 64 * 4, (void**)&h->w_out));
+  if (h->prec != AP_PREC_FP32_SIMT) AP_TRY(dalloc(out_umma_weight_bytes(h->onc), (void**)&h->w_out_img));
   AP_TRY(dalloc(256 * 4, (void**)&h->b_merge));
   AP_TRY(dalloc(h->onc * 4, (void**)&h->b_out));
   for (const LayerSpec& s : specs) {
@@ -639,7 +646,10 @@ int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const floa
       rc = launch_pack_weights(src, s.cout, 3, 7, 0, h->w_stem, 160, stem_off, nullptr, nullptr, st);
       if (rc == AP_OK && h->w_stem_img) rc = launch_pack_stem_umma(src, s.cout, stem_off, h->w_stem_img, st);
     }
-    else if (s.name == "model3.7") rc = launch_pack_out_weights(src, h->onc, h->w_out, st);
+    else if (s.name == "model3.7") {
+      rc = launch_pack_out_weights(src, h->onc, h->w_out, st);
+      if (rc == AP_OK && h->w_out_img) rc = launch_pack_out_umma(src, h->onc, h->w_out_img, st);
+    }
     else {
       LayerW lw;
       lw.cout = s.cout; lw.cin = s.cin; lw.k = s.k;
