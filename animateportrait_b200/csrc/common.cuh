@@ -82,6 +82,15 @@ struct ConvGeom {
   ConvTaps taps;
 };
 
+// ConvTranspose2d(k3,s2,p1,op1) as ONE stride-1 conv over the 2x2 input taps (dy,dx) in {0,1}^2 whose N dimension packs
+// `nph` output phases of `cols` channels each (weights of taps a phase does not use are zero): N = 256 keeps the
+// CTA-pair kernel efficient where four thin per-phase GEMMs are L2-fabric bound.  The epilogue routes column block
+// ph to output pixels (2i + py[ph], 2j + px[ph]).
+struct PhasePack {
+  int nph, cols;
+  int py[4], px[4];
+};
+
 struct SimtConvP {
   ConvGeom g;
   const float* in;  // fp32, NHWC (in_C channels per pixel, first channel in_coff) or NCHW
@@ -102,11 +111,14 @@ struct ApplyP {
   const double* stats2; int stat2_C, stat2_coff;
   const float* res_in;  // optional fp32 residual stream [B,H,W,C] added to the result
   float* res_out;       // optional: result written here as fp32 [B,H,W,C]
+  // optional residual read from an ACTIVATION buffer instead (the block input itself: fp32, or bf16 hi + lo)
+  int res_fmt; const void* res_p0; const void* res_p1; int res_C, res_pad;   // res_fmt = -1: absent
   int relu;
   int B, H, W, C;
   // destination (may be absent: fmt = -1)
   int fmt; void* d0; void* d1; int dC, dcoff, dpad;
   int halo_reflect;  // fill the halo ring by reflection (pad==1)
+  int l2_hints;      // raw loads evict_first (set by launch_apply from AP_NETG_L2_HINTS bit 1)
 };
 
 struct WarpP {
@@ -162,13 +174,18 @@ int launch_pack_weights(const float* src, int Cout, int Cin, int k, int transpos
 int64_t launches_get();
 void launches_add(int n);
 int launch_pack_out_weights(const float* src, int onc, float* dst, cudaStream_t st);
+// ConvTranspose2d weight [Cin][Cout][3][3] -> phase-packed [tap t][ph * Cout + co][Cin] bf16 hi / lo (see PhasePack);
+// taps are (tdy[t], tdx[t]), phases (pk.py, pk.px)
+int launch_pack_convT_phases(const float* src, int Cin, int Cout, const PhasePack& pk, int ntaps, const int* tdy,
+                             const int* tdx, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, cudaStream_t st);
 int launch_nchw_to_act(const float* src, const Act& dst, cudaStream_t st);  // debug conv helper
 
 // ---- tcgen05 conv ----
 struct UmmaConv;  // opaque launch record (tensor maps + params), see conv_umma.cu
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff,
                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int nprod,
-                     float* out_raw, int out_C, int out_coff, double* stats, int stat_C, int stat_coff);
+                     float* out_raw, int out_C, int out_coff, double* stats, int stat_C, int stat_coff,
+                     const PhasePack* pk = nullptr);
 void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
 int umma_init();  // resolves cuTensorMapEncodeTiled, sets func attributes

@@ -41,7 +41,8 @@ void launches_add(int n);
 struct alignas(64) UmmaParams {
   CUtensorMap tmA[2];  // hi, lo
   CUtensorMap tmW[2];
-  CUtensorMap tmO;     // fp32 output view (phase-strided for transposed convs)
+  CUtensorMap tmO[4];  // fp32 output view(s): one, or one per output phase of a phase-packed transposed conv
+  int phase_cols;      // 0, or channels per phase: column block c of the tile goes to tmO[c / phase_cols]
   int ntaps;
   int8_t dy[9], dx[9];
   uint8_t slab[9];
@@ -53,6 +54,7 @@ struct alignas(64) UmmaParams {
   // item list in units of tile GROUPS (CG consecutive 128-pixel tiles, one per CTA of the pair):
   // n_full whole groups with bn = Cout, then (groups - n_full) * split N-parts
   int n_full, split, n_items;
+  int l2_hints;  // bit 0: raw output stores evict_last (AP_NETG_L2_HINTS)
   int dbg;  // timing diagnostics only (AP_UMMA_DBG): 1 = no TMA loads after the first fill, 2 = no output stores, 4 = no statistics
 };
 
@@ -83,12 +85,44 @@ struct UmmaCfg {
   static constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
   static constexpr int STAGES_RAW = (226 * 1024 - 2 * 4 * 4096 - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 + (CG == 1 && BN <= 128 ? 4096 : 0);
 };
 
 struct Item {
   int img, ty, tx, n0, bn;
 };
+
+// Local item `li` of execution unit `unit` (CTA, or CTA pair) -> global item index, or -1 when the unit is done.
+// STRIDED: item = unit + li * nunits (neighbouring CTAs work on neighbouring tiles).  CONTIGUOUS (used where the
+// InstanceNorm statistics are accumulated on chip): the whole-wave part of the item list is dealt in runs, unit u
+// owning [u*K, (u+1)*K), so that consecutive items of a unit lie in the same image; tail items stay strided.
+template <bool CONTIGUOUS>
+__device__ __forceinline__ int item_at(const UmmaParams& p, int li, int unit, int nunits, int K) {
+  if (!CONTIGUOUS) {
+    const int it = unit + li * nunits;
+    return it < p.n_items ? it : -1;
+  }
+  if (li < K) return unit * K + li;
+  const int it = p.n_full + (li - K) * nunits + unit;
+  return it < p.n_items ? it : -1;
+}
+
+// Per-warp accumulation of the InstanceNorm statistics in shared memory across the items of one image: one fp64
+// atomic per (channel, warp, image run) instead of one per (channel, warp, tile).  fp64 atomics on one address
+// serialise in L2 (~15-30 ns each); layers with few channels and thousands of tiles were bound by exactly that
+// (profiles/r01_stat_atomics.md: 128->64 transposed conv 307 -> 138 us without statistics).
+constexpr int STAT_ACC_COLS = 128;
+constexpr int STAT_ACC_BYTES = 4 * 2 * STAT_ACC_COLS * 4;  // 4 epilogue warps x {sum, sumsq} x 128 channels x fp32
+
+__device__ __forceinline__ void stat_flush(float* sacc, double* stats, int stat_C, int stat_coff, int img, int ncols, int lane) {
+  for (int c = lane; c < ncols; c += 32) {
+    double* dst = stats + ((size_t)img * stat_C + stat_coff + c) * 2;
+    atomicAdd(dst, (double)sacc[c]);
+    atomicAdd(dst + 1, (double)sacc[STAT_ACC_COLS + c]);
+    sacc[c] = 0.f;
+    sacc[STAT_ACC_COLS + c] = 0.f;
+  }
+}
 
 // ---- single-CTA kernel (cta_group::1): one CTA per 128-pixel tile; used for the N <= 128 layers ----
 __device__ __forceinline__ Item decode_item1(const UmmaParams& p, int item, int BN) {
@@ -127,11 +161,14 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = p.ntaps * p.kchunks;
+  constexpr bool ACC = BN <= STAT_ACC_COLS;  // statistics accumulated on chip, contiguous item runs
+  const int Krun = ACC ? p.n_full / (int)gridDim.x : 0;
+  float* sacc_all = reinterpret_cast<float*>(epi_gen + EPI_BYTES + 256);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[0]) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO[0]) : "memory");
     if (NPROD == 3) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[1]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[1]) : "memory");
@@ -161,7 +198,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int li = 0;; ++li) {
+        const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
+        if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
         const int nbox = w.bn >> 6;
@@ -194,7 +233,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t cnt = 0, local = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+      for (int li = 0;; ++li, ++local) {
+        const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
+        if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
         // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
@@ -244,9 +285,23 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     const int yy = row0 / p.TW, xx0 = row0 - yy * p.TW;
     uint8_t* slab_gen = epi_gen + q * (EPI_SLABS * 4096);
     const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
+    const uint64_t opol = (p.l2_hints & 1) ? l2_policy_evict_last() : 0;  // raw output is re-read by the next kernel
     uint32_t local = 0, blk = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++local) {
+    float* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
+    int simg = -1;
+    if (ACC) {
+      for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0.f;
+      __syncwarp();
+    }
+    for (int li = 0;; ++li, ++local) {
+      const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
+      if (item < 0) break;
       const Item w = decode_item1(p, item, BN);
+      const bool acc_item = ACC && w.bn == BN;  // N-split tail items use direct atomics
+      if (ACC && simg >= 0 && (w.img != simg || !acc_item)) {
+        stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, BN, lane);
+        simg = -1;
+      }
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
@@ -257,21 +312,28 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
-        epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
+        epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[0], p.out_coff + w.n0 + c0, ox, oy, w.img, opol);
         if (strow != nullptr) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
           const float cs = butterfly_colsum(v, lane);
           const float cq = butterfly_colsum(sq, lane);
-          atomicAdd(strow + (size_t)c0 * 2, (double)cs);
-          atomicAdd(strow + (size_t)c0 * 2 + 1, (double)cq);
+          if (acc_item) {
+            sacc[c0 + lane] += cs;
+            sacc[STAT_ACC_COLS + c0 + lane] += cq;
+            simg = w.img;
+          } else {
+            atomicAdd(strow + (size_t)c0 * 2, (double)cs);
+            atomicAdd(strow + (size_t)c0 * 2 + 1, (double)cq);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
     }
+    if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, BN, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
   }
   tc_fence_before();
@@ -306,7 +368,8 @@ __device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int B
 
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) runs tcgen05.mma.cta_group::2
 // with M = 256; each CTA stages its own A tile and half of the weight tile, the leader (cluster rank 0) issues.
-template <int BN, int NPROD, int CG>
+// PACKED (phase-packed transposed convs): statistics accumulated on chip over contiguous item runs, one staging slab.
+template <int BN, int NPROD, int CG, bool PACKED>
 __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   using Cfg = UmmaCfg<BN, NPROD, CG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -316,8 +379,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_s = smem_base + STAGES * Cfg::STAGE_BYTES;
   uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
-  constexpr int EPI_SLABS = EpiCfg<BN>::SLABS;
-  constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
+  constexpr int EPI_SLABS = PACKED ? 1 : EpiCfg<BN>::SLABS;
+  constexpr int EPI_BYTES = 4 * EPI_SLABS * 4096;
+  constexpr bool ACC = PACKED;
   const uint32_t bars = epi_s + EPI_BYTES;
   // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);
@@ -327,11 +391,13 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // pair (or CTA) index
   const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int Krun = ACC ? p.n_full / nunits : 0;
+  float* sacc_all = reinterpret_cast<float*>(epi_gen + EPI_BYTES + 256);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[0]) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO[0]) : "memory");
     if (NPROD == 3) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[1]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW[1]) : "memory");
@@ -370,7 +436,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     if (lane == 0) {
       const uint32_t full0 = (CG == 2) ? mapa_rank(bars, 0) : bars;  // full barriers live in the leader
       uint32_t cnt = 0;
-      for (int item = unit; item < p.n_items; item += nunits) {
+      for (int li = 0;; ++li) {
+        const int item = item_at<ACC>(p, li, unit, nunits, Krun);
+        if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, rank);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
         const int wrows = w.bn / CG;
@@ -415,7 +483,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     // ===================== MMA issuer (leader CTA of the pair only) =====================
     if (lane == 0 && rank == 0) {
       uint32_t cnt = 0, local = 0;
-      for (int item = unit; item < p.n_items; item += nunits, ++local) {
+      for (int li = 0;; ++li, ++local) {
+        const int item = item_at<ACC>(p, li, unit, nunits, Krun);
+        if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, 0);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
         // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
@@ -479,29 +549,52 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     uint8_t* slab_gen = epi_gen + q * (EPI_SLABS * 4096);
     const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
     const uint32_t tempty0 = (CG == 2) ? mapa_rank(bars + 144, 0) : bars + 144;
+    const uint64_t opol = (p.l2_hints & 1) ? l2_policy_evict_last() : 0;  // raw output is re-read by the next kernel
     uint32_t local = 0, blk = 0;
-    for (int item = unit; item < p.n_items; item += nunits, ++local) {
+    float* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
+    int simg = -1;
+    if (ACC) {
+      for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0.f;
+      __syncwarp();
+    }
+    for (int li = 0;; ++li, ++local) {
+      const int item = item_at<ACC>(p, li, unit, nunits, Krun);
+      if (item < 0) break;
       const Item w = decode_item(p, item, BN, CG, rank);
+      const bool acc_item = ACC && p.phase_cols > 0 && p.phase_cols <= STAT_ACC_COLS;
+      if (ACC && simg >= 0 && w.img != simg) {
+        stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
+        simg = -1;
+      }
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
       const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
-      double* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + w.n0 + lane) * 2 : nullptr;
+      double* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + lane) * 2 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
+        // phase-packed transposed conv: columns [ph * phase_cols, (ph+1) * phase_cols) are output phase ph
+        int ch = w.n0 + c0, phs = 0;
+        if (p.phase_cols) { phs = ch / p.phase_cols; ch -= phs * p.phase_cols; }
         if (!AP_DBG(p.dbg & 2))
-          epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, p.out_coff + w.n0 + c0, ox, oy, w.img);
+          epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[phs], p.out_coff + ch, ox, oy, w.img, opol);
         if (strow != nullptr && !AP_DBG(p.dbg & 4)) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
           const float cs = butterfly_colsum(v, lane);
           const float cq = butterfly_colsum(sq, lane);
-          atomicAdd(strow + (size_t)c0 * 2, (double)cs);
-          atomicAdd(strow + (size_t)c0 * 2 + 1, (double)cq);
+          if (acc_item) {  // the phases of a packed transposed conv fold onto the same channel
+            sacc[ch + lane] += cs;
+            sacc[STAT_ACC_COLS + ch + lane] += cq;
+            simg = w.img;
+          } else {
+            atomicAdd(strow + (size_t)ch * 2, (double)cs);
+            atomicAdd(strow + (size_t)ch * 2 + 1, (double)cq);
+          }
         }
       }
       tc_fence_before();
@@ -511,6 +604,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         else mbar_arrive(bars + 144 + 8 * acc);
       }
     }
+    if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
     __syncwarp();
   }
@@ -532,15 +626,24 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static int g_sms = 0;
 
+template <int BN, int NPROD, bool PACKED>
+constexpr size_t pair_smem() {
+  return UmmaCfg<BN, NPROD, 2>::SMEM - (PACKED ? (size_t)(EpiCfg<BN>::BYTES - 4 * 4096) - 4096 : 0);
+}
+
 static int g_dbg = 0;
+static int g_l2_hints = 0;
 static int g_pair = 1;  // CTA-pair (cta_group::2) kernels unless AP_NETG_CTA_PAIR=0
 
 template <int BN, int NPROD>
 static int set_attr() {
   AP_CUDA(cudaFuncSetAttribute(conv_umma1_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)UmmaCfg<BN, NPROD, 1>::SMEM));
-  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)UmmaCfg<BN, NPROD, 2>::SMEM));
+  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)pair_smem<BN, NPROD, false>()));
+  if (BN == 256)
+    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, NPROD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pair_smem<256, NPROD, true>()));
   return AP_OK;
 }
 
@@ -562,6 +665,8 @@ int umma_init() {
   AP_TRY((set_attr<256, 3>()));
   const char* e = getenv("AP_NETG_CTA_PAIR");
   g_pair = e ? atoi(e) : 1;  // 0: never, 1: where it wins (Cout = 256), 2: everywhere
+  const char* lh = getenv("AP_NETG_L2_HINTS");
+  g_l2_hints = lh ? atoi(lh) : 0;
   const char* d = getenv("AP_UMMA_DBG");
   g_dbg = d ? atoi(d) : 0;
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
@@ -613,7 +718,7 @@ static int max_pairs_of() {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2, false>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = 0;
   }
@@ -631,7 +736,7 @@ static int max_pairs(int BN, int nprod) {
 // out-of-bounds with zeros); reflect-padded ones address the haloed buffer (halo = in.pad >= conv pad).
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
                      const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, double* stats,
-                     int stat_C, int stat_coff) {
+                     int stat_C, int stat_coff, const PhasePack* pk) {
   AP_TRY(umma_init());
   AP_REQUIRE(in.fmt == FMT_BF16X2 || in.fmt == FMT_BF16, AP_ERR_INVALID, "umma conv needs bf16 activations");
   AP_REQUIRE(nprod == 1 || (nprod == 3 && in.fmt == FMT_BF16X2 && w_lo), AP_ERR_INVALID, "umma conv: nprod/format");
@@ -655,7 +760,11 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   const int pairs = g_pair ? max_pairs(g.Cout, nprod) : 0;
   // measured (profiles/r01_cta_pair.md): pairs win for N = 256 with the 3-product operands (-7..-13%), lose for
   // N <= 128 (+9..+18%) and for single-product bf16 (+8%: 512-cycle stages are too short for the pair handshake)
-  c->cg = (pairs > 0 && ntiles % 2 == 0 && ((g.Cout == 256 && nprod == 3) || g_pair == 2)) ? 2 : 1;
+  c->cg = (pairs > 0 && ntiles % 2 == 0 && ((g.Cout == 256 && nprod == 3) || g_pair == 2 || pk)) ? 2 : 1;
+  if (pk) {
+    AP_REQUIRE(c->cg == 2 && g.Cout == 256 && pk->nph * pk->cols == 256 && pk->cols % 32 == 0 && g.stride == 1, AP_ERR_UNSUPPORTED,
+               "phase-packed transposed conv needs the CTA-pair kernel and N = 256");
+  }
   const int wrows = g.Cout / c->cg;
   // activation maps
   const bool padded_view = g.reflect != 0;
@@ -671,15 +780,22 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   if (rc == AP_OK && nprod == 3)
     rc = tmap_encode(&p.tmA[1], 0, reinterpret_cast<const __nv_bfloat16*>(in.p1) + view_off, 4, adims, astr, abox, aes);
   // weight maps [slab][Cout][Cin], boxes of 64 output channels
+  const int wslabs = pk ? g.taps.n : 9;
   for (int i = 0; i < g.taps.n; ++i)
-    AP_REQUIRE(g.taps.slab[i] < 9, AP_ERR_INVALID, "umma conv: only 3x3 weight slabs are packed for tcgen05");
-  const uint64_t wdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 9};
+    AP_REQUIRE(g.taps.slab[i] < wslabs, AP_ERR_INVALID, "umma conv: weight slab %d of %d", g.taps.slab[i], wslabs);
+  const uint64_t wdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)wslabs};
   const uint64_t wstr[2] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * g.Cout * 2};
   const uint32_t wbox[3] = {64, (uint32_t)(wrows < 64 ? wrows : 64), 1};
   const uint32_t wes[3] = {1, 1, 1};
   if (rc == AP_OK) rc = tmap_encode(&p.tmW[0], 0, w_hi, 3, wdims, wstr, wbox, wes);
   if (rc == AP_OK && nprod == 3) rc = tmap_encode(&p.tmW[1], 0, w_lo, 3, wdims, wstr, wbox, wes);
-  if (rc == AP_OK) rc = tmap_encode_out(&p.tmO, out_raw, g.B, g.Hout, g.Wout, out_C, g.os, g.py, g.px);
+  p.phase_cols = pk ? pk->cols : 0;
+  if (pk) {
+    for (int i = 0; i < pk->nph && rc == AP_OK; ++i)
+      rc = tmap_encode_out(&p.tmO[i], out_raw, g.B, 2 * g.Hin, 2 * g.Win, out_C, 2, pk->py[i], pk->px[i]);
+  } else if (rc == AP_OK) {
+    rc = tmap_encode_out(&p.tmO[0], out_raw, g.B, g.Hout, g.Wout, out_C, g.os, g.py, g.px);
+  }
   if (rc != AP_OK) { delete c; return rc; }
 
   p.ntaps = g.taps.n;
@@ -696,7 +812,8 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   p.tiles_x = g.Wv / TW; p.tiles_y = g.Hv / TH;
   p.stride = g.stride;
   p.out_coff = out_coff;
-  p.stats = stats; p.stat_C = stat_C; p.stat_coff = stat_coff;
+  p.stats = (g_dbg & 8) ? nullptr : stats;  // AP_UMMA_DBG bit 3 (timing probe only): no InstanceNorm statistics at all
+  p.stat_C = stat_C; p.stat_coff = stat_coff;
   // item list: whole waves of full tile groups, the remainder split along N so the tail fills the machine
   const int groups = ntiles / c->cg;
   const int G = c->cg == 2 ? pairs : (g_sms > 0 ? g_sms : 148);  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
@@ -707,6 +824,7 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   }
   p.split = split;
   p.dbg = g_dbg;
+  p.l2_hints = g_l2_hints;
   p.n_full = groups - rem;
   p.n_items = p.n_full + rem * split;
   c->grid = dim3((unsigned)((p.n_items < G ? p.n_items : G) * c->cg), 1);
@@ -725,7 +843,8 @@ static int launch_one(const UmmaConv* c, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = c->grid;
     cfg.blockDim = dim3(192, 1, 1);
-    cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, 2>::SMEM;
+    const bool packed = c->p.phase_cols > 0 && BN == 256;
+    cfg.dynamicSmemBytes = packed ? pair_smem<256, NPROD, true>() : pair_smem<BN, NPROD, false>();
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -734,7 +853,8 @@ static int launch_one(const UmmaConv* c, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2>, c->p));
+    if (packed) AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, NPROD, 2, true>, c->p));
+    else AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2, false>, c->p));
   }
   launches_add(1);
   return AP_OK;

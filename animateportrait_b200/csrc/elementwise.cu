@@ -1,5 +1,7 @@
 // HBM-bound kernels of the generator: InstanceNorm apply (+ReLU, +residual, +halo, +bf16 hi/lo split),
 // the fused double feature warp, weight packing and the debug tap reader.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ap {
@@ -60,13 +62,25 @@ __device__ __forceinline__ void store_pixel(const Dst& d, int n, int y, int x, i
 // flight per thread.  H and W are powers of two (64/128/256): no integer division anywhere.
 // ------------------------------------------------------------------------------------------------
 
+// raw conv output is dead after the apply pass: do not let it displace the operands of the next conv in L2
+__device__ __forceinline__ float4 ld_stream_evict_first(const float* p) {
+  float4 r;
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+
 __device__ __forceinline__ float4 ld_stream(const float* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
 
-// MODE 0: IN (or bias) [+ReLU];  1: + InstanceNorm'ed second operand (ResnetBlock2 shortcut);  2: + fp32 residual.
+// MODE 0: IN (or bias) [+ReLU];  1: + InstanceNorm'ed second operand (ResnetBlock2 shortcut);  2: + fp32 residual
+// stream;  3: + residual read from the block's input activation (fp32, or bf16 hi + lo = 16 mantissa bits).
 // 85 registers at most (3 CTAs = 24 warps per SM, each thread with 4-12 independent 16-byte loads in flight) and
 // CTAs of only 8 pixel passes, so that the grid is several balanced waves instead of 1.7 fat ones.
 template <int TPP, int MODE>
@@ -94,15 +108,31 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   const float* raw2 = (MODE == 1) ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
   const float* rin = (MODE == 2) ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
   float* rout = p.res_out ? p.res_out + ((size_t)n * HW) * p.C + c : nullptr;
+  const int rWp = p.W + 2 * p.res_pad;
+  const size_t rbase = (size_t)n * (p.H + 2 * p.res_pad);
 #pragma unroll 1
   for (int k0 = 0; k0 < APPLY_PIX_PER_CTA; k0 += 4 * NY) {
     float4 v[4], u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int pix = pix0 + k0 + j * NY;
-      v[j] = ld_stream(raw + (size_t)pix * p.raw_C);
-      if (MODE == 1) u[j] = ld_stream(raw2 + (size_t)pix * p.raw2_C);
+      v[j] = p.l2_hints ? ld_stream_evict_first(raw + (size_t)pix * p.raw_C) : ld_stream(raw + (size_t)pix * p.raw_C);
+      if (MODE == 1) u[j] = p.l2_hints ? ld_stream_evict_first(raw2 + (size_t)pix * p.raw2_C) : ld_stream(raw2 + (size_t)pix * p.raw2_C);
       if (MODE == 2) u[j] = ld_stream(rin + (size_t)pix * p.C);
+      if (MODE == 3) {
+        const size_t roff = ((rbase + (pix >> logW) + p.res_pad) * rWp + (pix & (p.W - 1)) + p.res_pad) * p.res_C + c;
+        if (p.res_fmt == FMT_F32) {
+          u[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res_p0) + roff);
+        } else {
+          const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res_p0) + roff);
+          const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.res_p1) + roff);
+          // bf16 -> fp32 is a 16-bit shift
+          u[j].x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+          u[j].y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+          u[j].z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+          u[j].w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -119,7 +149,7 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
         o.z += (u[j].z - mean2[2]) * rstd2[2];
         o.w += (u[j].w - mean2[3]) * rstd2[3];
       }
-      if (MODE == 2) { o.x += u[j].x; o.y += u[j].y; o.z += u[j].z; o.w += u[j].w; }
+      if (MODE >= 2) { o.x += u[j].x; o.y += u[j].y; o.z += u[j].z; o.w += u[j].w; }
       if (rout) *reinterpret_cast<float4*>(rout + (size_t)pix * p.C) = o;
       if (p.fmt >= 0) store_pixel(d, n, pix >> logW, pix & (p.W - 1), c, o);
     }
@@ -130,14 +160,25 @@ template <int TPP>
 static void launch_apply_tpp(const ApplyP& p, dim3 grid, cudaStream_t st) {
   if (p.raw2) apply_kernel<TPP, 1><<<grid, 256, 0, st>>>(p);
   else if (p.res_in) apply_kernel<TPP, 2><<<grid, 256, 0, st>>>(p);
+  else if (p.res_fmt >= 0) apply_kernel<TPP, 3><<<grid, 256, 0, st>>>(p);
   else apply_kernel<TPP, 0><<<grid, 256, 0, st>>>(p);
 }
 
-int launch_apply(const ApplyP& p, cudaStream_t st) {
+static int g_apply_hints = -1;
+
+int launch_apply(const ApplyP& p_in, cudaStream_t st) {
+  if (g_apply_hints < 0) {
+    const char* e = getenv("AP_NETG_L2_HINTS");
+    g_apply_hints = e ? ((atoi(e) >> 1) & 1) : 0;
+  }
+  ApplyP p = p_in;
+  p.l2_hints = g_apply_hints;
   AP_REQUIRE(p.C == 16 || p.C == 128 || p.C == 256, AP_ERR_INVALID, "apply: C=%d (16, 128 or 256)", p.C);
   AP_REQUIRE(p.raw_C % 4 == 0 && p.raw_coff % 4 == 0, AP_ERR_INVALID, "apply: raw channel layout not 16B aligned");
   AP_REQUIRE(p.fmt < 0 || (p.dC % 4 == 0 && p.dcoff % 4 == 0), AP_ERR_INVALID, "apply: dst channel layout");
-  AP_REQUIRE(!(p.raw2 && p.res_in), AP_ERR_INVALID, "apply: shortcut operand and residual stream are exclusive");
+  AP_REQUIRE((p.raw2 != nullptr) + (p.res_in != nullptr) + (p.res_fmt >= 0) <= 1, AP_ERR_INVALID,
+             "apply: shortcut operand and residual stream are exclusive");
+  AP_REQUIRE(p.res_fmt < 0 || p.res_fmt == FMT_F32 || p.res_fmt == FMT_BF16X2, AP_ERR_INVALID, "apply: residual format");
   const int ppc = 8 * (256 / (p.C / 4));  // pixels per CTA (matches APPLY_PIX_PER_CTA in the kernel)
   AP_REQUIRE((p.W & (p.W - 1)) == 0 && (p.H * p.W) % ppc == 0, AP_ERR_INVALID, "apply: %dx%d", p.H, p.W);
   dim3 grid(p.H * p.W / ppc, p.B);
@@ -353,6 +394,41 @@ int launch_pack_weights(const float* src, int Cout, int Cin, int k, int transpos
   const int blocks = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
   pack_weights_kernel<<<blocks, 256, 0, st>>>(src, Cout, Cin, k, transposed, dst_simt, simt_C, simt_coff, dst_hi,
                                               dst_lo);
+  AP_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
+struct PackT {
+  PhasePack pk;
+  int ntaps, tdy[4], tdx[4];
+};
+
+// kernel row used by output phase p (0/1) at input offset d (0/1):  p=0: d=0 -> k=1;  p=1: d=1 -> k=0, d=0 -> k=2
+__device__ __forceinline__ int convT_k(int p, int d) { return p == 0 ? (d == 0 ? 1 : -1) : (d == 1 ? 0 : 2); }
+
+__global__ void pack_convT_phases_kernel(const float* __restrict__ src, int Cin, int Cout, PackT q, __nv_bfloat16* dst_hi,
+                                         __nv_bfloat16* dst_lo) {
+  const int N = q.pk.nph * Cout;
+  const size_t total = (size_t)q.ntaps * N * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int n = (int)((i / Cin) % N);
+    const int t = (int)(i / ((size_t)Cin * N));
+    const int ph = n / Cout, co = n - ph * Cout;
+    const int ky = convT_k(q.pk.py[ph], q.tdy[t]), kx = convT_k(q.pk.px[ph], q.tdx[t]);
+    const float w = (ky >= 0 && kx >= 0) ? src[((size_t)ci * Cout + co) * 9 + ky * 3 + kx] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    dst_hi[i] = h;
+    if (dst_lo) dst_lo[i] = __float2bfloat16_rn(w - __bfloat162float(h));
+  }
+}
+
+int launch_pack_convT_phases(const float* src, int Cin, int Cout, const PhasePack& pk, int ntaps, const int* tdy,
+                             const int* tdx, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, cudaStream_t st) {
+  PackT q{};
+  q.pk = pk; q.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { q.tdy[t] = tdy[t]; q.tdx[t] = tdx[t]; }
+  pack_convT_phases_kernel<<<592, 256, 0, st>>>(src, Cin, Cout, q, dst_hi, dst_lo);
   AP_CUDA(cudaGetLastError());
   return AP_OK;
 }

@@ -61,8 +61,17 @@ static std::vector<LayerSpec> layer_specs(int onc) {
   return v;
 }
 
+struct PackedT {  // phase-packed weights of a transposed conv (common.cuh: PhasePack)
+  PhasePack pk;
+  int ntaps;
+  int tdy[4], tdx[4];
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+};
+
 struct LayerW {
   int cout = 0, cin = 0, k = 0;
+  std::vector<PackedT> packT;     // transposed convs on the tensor-core path
   float* simt = nullptr;          // [slab][Cin][Cout]
   __nv_bfloat16* hi = nullptr;    // [slab][Cout][Cin]
   __nv_bfloat16* lo = nullptr;
@@ -106,6 +115,47 @@ struct Plan {
   }
 };
 
+
+// Phase-packed weights of one ConvTranspose2d layer.  Cout = 64: all four phases in one N = 256 conv over the four
+// input taps.  Cout = 128: phases (0,0),(0,1) need only the two taps of the same input row; (1,0),(1,1) need all four.
+static int make_packed_convT(const float* src_dev, int cin, int cout, bool with_lo, cudaStream_t st, std::vector<void*>* owned,
+                             std::vector<PackedT>* out) {
+  AP_REQUIRE(cout == 64 || cout == 128, AP_ERR_UNSUPPORTED, "phase-packed transposed conv: Cout=%d", cout);
+  const int npack = cout == 64 ? 1 : 2;
+  for (int k = 0; k < npack; ++k) {
+    PackedT pt{};
+    pt.pk.cols = cout;
+    pt.pk.nph = 256 / cout;
+    for (int i = 0; i < pt.pk.nph; ++i) {
+      const int ph = (npack == 1) ? i : 2 * k + i;
+      pt.pk.py[i] = ph >> 1;
+      pt.pk.px[i] = ph & 1;
+    }
+    pt.ntaps = (npack == 2 && k == 0) ? 2 : 4;
+    for (int t = 0; t < pt.ntaps; ++t) { pt.tdy[t] = t >> 1; pt.tdx[t] = t & 1; }
+    const size_t pe = (size_t)pt.ntaps * 256 * cin;
+    AP_CUDA(cudaMalloc((void**)&pt.hi, pe * 2));
+    owned->push_back(pt.hi);
+    if (with_lo) {
+      AP_CUDA(cudaMalloc((void**)&pt.lo, pe * 2));
+      owned->push_back(pt.lo);
+    }
+    AP_TRY(launch_pack_convT_phases(src_dev, cin, cout, pt.pk, pt.ntaps, pt.tdy, pt.tdx, pt.hi, pt.lo, st));
+    out->push_back(pt);
+  }
+  return AP_OK;
+}
+
+static ConvGeom geom_convT_packed(int B, int Hin, int Cin, const PackedT& pt) {
+  ConvGeom g{};
+  g.B = B; g.Hin = Hin; g.Win = Hin; g.Cin = Cin;
+  g.Hv = Hin; g.Wv = Hin; g.stride = 1; g.reflect = 0; g.Cout = 256;
+  g.os = 1; g.py = 0; g.px = 0; g.Hout = 2 * Hin; g.Wout = 2 * Hin;
+  g.taps.n = pt.ntaps;
+  for (int t = 0; t < pt.ntaps; ++t) { g.taps.dy[t] = (int8_t)pt.tdy[t]; g.taps.dx[t] = (int8_t)pt.tdx[t]; g.taps.slab[t] = (uint8_t)t; }
+  return g;
+}
+
 }  // namespace ap
 
 using namespace ap;
@@ -118,6 +168,7 @@ struct ap_netg {
   bool profiling = false;
   bool overlap = true;  // run independent branches on side streams (AP_NETG_OVERLAP=0 turns it off)
   bool out_umma = true; // tcgen05 output stage (AP_NETG_OUT_UMMA=0: CUDA-core kernel)
+  bool convt_packed = true;  // transposed convs as one phase-packed N=256 conv (AP_NETG_CONVT_PACKED=0: four phase convs)
   std::vector<cudaEvent_t> ev;      // ev[0] = start, ev[i+1] = after launch i
   std::vector<int> ev_class;        // class of launch i
   std::vector<double> ev_flops;
@@ -146,6 +197,8 @@ struct Inputs {
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static ConvGeom geom_convT_phase_(int B, int Hin, int Cin, int Cout, int py, int px);
 
 struct Runner {
   ap_netg* h;
@@ -272,6 +325,28 @@ struct Runner {
     AP_TRY(umma_conv_launch(pl->convs.at(conv_i++), st));
     return mark((g.stride == 1 && g.os == 1) ? CL_TRUNK : CL_STRIDED, conv_flops(g));
   }
+  // ConvTranspose2d(k3,s2,p1,op1) (networks.py:1271-1274): one or two phase-packed N = 256 convs on the CTA-pair
+  // kernel, or (CUDA-core mode / AP_NETG_CONVT_PACKED=0) four per-phase convs
+  int convT(const Act& in, const LayerW& w, const Raw& out, int Hin, int Cin, int Cout) {
+    if (h->prec == AP_PREC_FP32_SIMT || !h->convt_packed || w.packT.empty()) {
+      for (int ph_ = 0; ph_ < 4; ++ph_) AP_TRY(conv(geom_convT_phase_(pl->B, Hin, Cin, Cout, ph_ >> 1, ph_ & 1), in, 0, w, out, 0));
+      return AP_OK;
+    }
+    if (ph == PH_SIZE) return AP_OK;
+    for (const PackedT& pt : w.packT) {
+      if (ph == PH_BUILD) {
+        const ConvGeom g = geom_convT_packed(pl->B, Hin, Cin, pt);
+        UmmaConv* c = nullptr;
+        AP_TRY(umma_conv_create(&c, g, in, 0, pt.hi, pt.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C, 0, out.stats,
+                                out.C, 0, &pt.pk));
+        pl->convs.push_back(c);
+      } else {
+        AP_TRY(umma_conv_launch(pl->convs.at(conv_i++), st));
+        AP_TRY(mark(CL_STRIDED, 2.0 * pl->B * Hin * Hin * (double)Cin * Cout * 9 / (double)w.packT.size()));
+      }
+    }
+    return AP_OK;
+  }
   // thin CUDA-core layers (stems, landmark branch): fp32 input, NCHW or NHWC
   int conv_thin(const ConvGeom& g, const float* in, int nchw, int in_C, const float* wpk, const Raw& out) {
     if (ph != PH_EXEC) return AP_OK;
@@ -285,7 +360,7 @@ struct Runner {
     return mark(g.taps.n == 49 ? CL_STEM : CL_LAND, conv_flops(g));
   }
   int apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias = nullptr,
-            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr) {
+            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr, const Act* res_act = nullptr) {
     if (ph != PH_EXEC) return AP_OK;
     ApplyP p{};
     p.raw = r.p; p.raw_C = r.C; p.raw_coff = rcoff;
@@ -293,6 +368,8 @@ struct Runner {
     p.bias = bias;
     if (r2) { p.raw2 = r2->p; p.raw2_C = r2->C; p.raw2_coff = 0; p.stats2 = r2->stats; p.stat2_C = r2->C; p.stat2_coff = 0; }
     p.res_in = res_in; p.res_out = res_out;
+    p.res_fmt = -1;
+    if (res_act) { p.res_fmt = res_act->fmt; p.res_p0 = res_act->p0; p.res_p1 = res_act->p1; p.res_C = res_act->C; p.res_pad = res_act->pad; }
     p.relu = relu;
     p.B = r.B; p.H = r.H; p.W = r.W; p.C = C;
     if (dst) { p.fmt = dst->fmt; p.d0 = dst->p0; p.d1 = dst->p1; p.dC = dst->C; p.dcoff = dcoff; p.dpad = dst->pad; }
@@ -325,6 +402,8 @@ static ConvGeom geom_conv(int B, int Hin, int Cin, int Cout, int k, int stride, 
   g.taps = make_taps_conv(k, pad, 0);
   return g;
 }
+static ConvGeom geom_convT_phase(int B, int Hin, int Cin, int Cout, int py, int px);
+static ConvGeom geom_convT_phase_(int B, int Hin, int Cin, int Cout, int py, int px) { return geom_convT_phase(B, Hin, Cin, Cout, py, px); }
 static ConvGeom geom_convT_phase(int B, int Hin, int Cin, int Cout, int py, int px) {
   ConvGeom g{};
   g.B = B; g.Hin = Hin; g.Win = Hin; g.Cin = Cin;
@@ -346,13 +425,26 @@ int Runner::run(const Inputs& in) {
   if (ph == PH_EXEC && pl->sarena_bytes) AP_CUDA(cudaMemsetAsync(pl->sarena, 0, pl->sarena_bytes, st));
   cudaStream_t s1 = side(0), s2 = side(1), s3 = side(2);
 
-  // trunk buffers (the landmark branch writes its 2 x 16 channels of XL early, on a side stream)
-  Act XL = act(B, 64, 64, 288, hp, afmt);  // cat[x, l1, l2] (networks.py:1335)
-  Act X = act(B, 64, 64, 256, hp, afmt);
+  // trunk buffers: Xb[0] = merge output, Xb[i+1] = output of block i.  The inputs of the three ResnetBlock2 carry
+  // 2 x 16 extra channels, cat[x, l1, l2] (networks.py:1335); the landmark branch fills them early on a side stream.
+  // Tensor-core modes: the residual stream is a separate fp32 buffer per block (xres) and the operand buffers are
+  // reused in place (XL for the 288-channel inputs, X for the others) so that they stay L2-resident.  Reading the
+  // residual back from the bf16 hi/lo operand planes instead was measured slower (two 8-byte loads per thread and
+  // fresh output lines every block: in_apply 1.34 -> 1.50 ms/step at B=16) and is only used by the CUDA-core mode,
+  // whose operands are fp32 anyway.
+  const bool res_from_act = (prec == AP_PREC_FP32_SIMT);
+  Act Xb[10];
+  if (res_from_act) {
+    for (int i = 0; i < 10; ++i) Xb[i] = act(B, 64, 64, (i % 3 == 0 && i < 9) ? 288 : 256, i == 9 ? 0 : hp, afmt);
+  } else {
+    const Act XL = act(B, 64, 64, 288, hp, afmt), X = act(B, 64, 64, 256, hp, afmt), D0 = act(B, 64, 64, 256, 0, afmt);
+    for (int i = 0; i < 9; ++i) Xb[i] = (i % 3 == 0) ? XL : X;
+    Xb[9] = D0;
+  }
   Act T = act(B, 64, 64, 256, hp, afmt);
-  Act D0 = act(B, 64, 64, 256, 0, afmt);   // decoder input
-  float* xres[10];
-  for (int i = 0; i < 10; ++i) xres[i] = (float*)alloc((size_t)B * 64 * 64 * 256 * sizeof(float));
+  float* xres[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!res_from_act)
+    for (int i = 0; i < 10; ++i) xres[i] = (float*)alloc((size_t)B * 64 * 64 * 256 * sizeof(float));
 
   // ---- landmark branch on land1 and land2 as one batch of 2B maps (networks.py:1280-1282, 1331-1332) ----
   {
@@ -375,8 +467,8 @@ int Runner::run(const Inputs& in) {
         v.p = rl2.p + (size_t)li * B * 64 * 64 * 16;
         v.stats = rl2.stats + (size_t)li * B * 16 * 2;
       }
-      AP_TRY(apply(v, 0, 16, 0, &XL, 256 + 16 * li, 1));
-      tap_act(li == 0 ? "land1" : "land2", XL, 256 + 16 * li, 16);
+      for (int k = 0; k < (res_from_act ? 9 : 3); k += 3) AP_TRY(apply(v, 0, 16, 0, &Xb[k], 256 + 16 * li, 1));
+      tap_act(li == 0 ? "land1" : "land2", Xb[0], 256 + 16 * li, 16);
     }
     on(main_st);
   }
@@ -451,8 +543,9 @@ int Runner::run(const Inputs& in) {
   // ---- merge: Conv3 768->256, zero pad, bias kept, no norm (networks.py:1251,1330) ----
   Raw rM = raw(B, 64, 64, 256, false);
   AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0));
-  AP_TRY(apply(rM, 0, 256, 0, &XL, 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
-  tap_f32("merge", xres[0], B, 64, 64, 256);
+  AP_TRY(apply(rM, 0, 256, 0, &Xb[0], 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
+  if (res_from_act) tap_act("merge", Xb[0], 0, 256);
+  else tap_f32("merge", xres[0], B, 64, 64, 256);
 
   AP_TRY(order_after(main_st, s3));
 
@@ -460,9 +553,9 @@ int Runner::run(const Inputs& in) {
   for (int i = 0; i < 9; ++i) {
     const std::string b = "model2." + std::to_string(i);
     const bool b2 = (i % 3) == 0;
-    const Act& src = b2 ? XL : X;
+    const Act& src = Xb[i];
     const int cin = b2 ? 288 : 256;
-    const Act* dst = (i == 8) ? &D0 : (((i + 1) % 3 == 0) ? &XL : &X);
+    const Act* dst = &Xb[i + 1];
     const int dst_halo = (i == 8) ? 0 : 1;
     Raw rs;
     Raw r1 = raw(B, 64, 64, 256, true);
@@ -481,21 +574,21 @@ int Runner::run(const Inputs& in) {
     AP_TRY(conv(geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, 0, W(b + ".conv_block.5"), r2, 0));
     if (b2) AP_TRY(order_after(main_st, s1));
     if (b2) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1]));
+    else if (res_from_act) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, nullptr, nullptr, &src));
     else AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, xres[i], xres[i + 1]));
     const std::string tn = "block" + std::to_string(i);
-    tap_f32(tn.c_str(), xres[i + 1], B, 64, 64, 256);
+    if (res_from_act) tap_act(tn.c_str(), *dst, 0, 256);
+    else tap_f32(tn.c_str(), xres[i + 1], B, 64, 64, 256);
   }
 
   // ---- decoder (networks.py:1268-1279): two ConvT as 4 output phases each, then the 7x7 output conv ----
   Raw ru0 = raw(B, 128, 128, 128, true);
-  for (int ph_ = 0; ph_ < 4; ++ph_)
-    AP_TRY(conv(geom_convT_phase(B, 64, 256, 128, ph_ >> 1, ph_ & 1), D0, 0, W("model3.0"), ru0, 0));
+  AP_TRY(convT(Xb[9], W("model3.0"), ru0, 64, 256, 128));
   tap_raw("up0", ru0, 0, 128, 1);
   Act U0 = act(B, 128, 128, 128, 0, afmt);
   AP_TRY(apply(ru0, 0, 128, 1, &U0, 0, 0));
   Raw ru1 = raw(B, 256, 256, 64, true);
-  for (int ph_ = 0; ph_ < 4; ++ph_)
-    AP_TRY(conv(geom_convT_phase(B, 128, 128, 64, ph_ >> 1, ph_ & 1), U0, 0, W("model3.3"), ru1, 0));
+  AP_TRY(convT(U0, W("model3.3"), ru1, 128, 128, 64));
   tap_raw("up1", ru1, 0, 64, 1);
   if (ph == PH_EXEC) {
     OutConvP p{};
@@ -567,6 +660,8 @@ int ap_netg_create(ap_netg** handle, int output_nc, int precision, int device) {
   h->onc = output_nc; h->prec = precision; h->device = device;
   const char* ov = getenv("AP_NETG_OVERLAP");
   h->overlap = !(ov && ov[0] == '0');
+  const char* cp = getenv("AP_NETG_CONVT_PACKED");
+  h->convt_packed = !(cp && cp[0] == '0');
   const char* ou = getenv("AP_NETG_OUT_UMMA");
   h->out_umma = !(ou && ou[0] == '0');
   *handle = h;
@@ -680,6 +775,8 @@ int ap_netg_load_weights(ap_netg* h, int n, const char* const* names, const floa
       if (rc == AP_OK && !simt && h->prec == AP_PREC_FP32X3) rc = dalloc(elems * 2, (void**)&lw.lo);
       if (rc == AP_OK)
         rc = launch_pack_weights(src, s.cout, s.cin, s.k, s.transposed ? 1 : 0, lw.simt, s.cout, 0, lw.hi, lw.lo, st);
+      if (rc == AP_OK && s.transposed && !simt)
+        rc = make_packed_convT(src, s.cin, s.cout, h->prec == AP_PREC_FP32X3, st, &h->owned, &lw.packT);
       h->w[s.name] = lw;
     }
     if (rc != AP_OK) break;
@@ -877,7 +974,19 @@ int ap_conv2d_debug(int impl, int device, int B, int H, int W, int Cin, int Cout
   std::vector<UmmaConv*> convs;
   if (rc == AP_OK) rc = launch_nchw_to_act(x, in, st);
   if (rc == AP_OK) rc = launch_pack_weights(w, Cout, Cin, ksize, transposed, lw.simt, Cout, 0, lw.hi, lw.lo, st);
-  const int nph = transposed ? 4 : 1;
+  std::vector<PackedT> packT;
+  const char* cp = getenv("AP_NETG_CONVT_PACKED");
+  const bool packed = transposed && tc && (Cout == 64 || Cout == 128) && !(cp && cp[0] == '0');
+  if (rc == AP_OK && packed) rc = make_packed_convT(w, Cin, Cout, impl == AP_PREC_FP32X3, st, &tmp, &packT);
+  if (packed) {
+    for (size_t k = 0; k < packT.size() && rc == AP_OK; ++k) {
+      UmmaConv* c = nullptr;
+      rc = umma_conv_create(&c, geom_convT_packed(B, H, Cin, packT[k]), in, 0, packT[k].hi, packT[k].lo,
+                            impl == AP_PREC_FP32X3 ? 3 : 1, out.p, Cout, 0, out.stats, Cout, 0, &packT[k].pk);
+      if (rc == AP_OK) { convs.push_back(c); rc = umma_conv_launch(c, st); }
+    }
+  }
+  const int nph = packed ? 0 : (transposed ? 4 : 1);
   for (int ph = 0; ph < nph && rc == AP_OK; ++ph) {
     ConvGeom g = transposed ? geom_convT_phase(B, H, Cin, Cout, ph >> 1, ph & 1)
                             : geom_conv(B, H, Cin, Cout, ksize, stride, pad, pad_mode);

@@ -180,6 +180,23 @@ static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// L2 eviction-priority policies for stores / loads whose reuse distance is known
+static __device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+static __device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+static __device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                                         uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+               : "memory");
+}
 static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 static __device__ __forceinline__ void bulk_wait_read() {
@@ -196,7 +213,8 @@ static __device__ __forceinline__ void bulk_wait() {
 // `pending` = how many earlier stores of this warp may still be reading OTHER slabs (NSLAB - 1).
 template <int PENDING>
 static __device__ __forceinline__ void epi_store_block(const float (&v)[32], uint8_t* slab_gen, uint32_t slab_s, int lane,
-                                                       const CUtensorMap* omap, int c, int x, int y, int n) {
+                                                       const CUtensorMap* omap, int c, int x, int y, int n,
+                                                       uint64_t policy = 0) {
   if (lane == 0) bulk_wait_read<PENDING>();  // the store that last used this slab has finished reading it
   __syncwarp();
   uint8_t* rowp = slab_gen + lane * 128;
@@ -207,7 +225,8 @@ static __device__ __forceinline__ void epi_store_block(const float (&v)[32], uin
   fence_proxy_async();
   __syncwarp();
   if (lane == 0) {
-    tma_store_4d(omap, slab_s, c, x, y, n);
+    if (policy) tma_store_4d_hint(omap, slab_s, c, x, y, n, policy);
+    else tma_store_4d(omap, slab_s, c, x, y, n);
     bulk_commit();
   }
 }

@@ -205,21 +205,24 @@ def main():
     out_host = torch.empty((B, onc, 256, 256), dtype=torch.float32, pin_memory=True)
     h2d = sum(t_.numel() * 4 for t_ in host_sets[0])
     d2h = out_host.numel() * 4
-    if world == 1:
-        for i in range(2):
-            net.forward_host(*host_sets[i % N_INPUT_SETS], out=out_host)
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for i in range(e2e_steps):
-            net.forward_host(*host_sets[i % N_INPUT_SETS], out=out_host)  # H2D + forward + D2H + sync inside
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        e2e = {"value": B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "path": "ap_netg_forward_host: pinned host inputs -> H2D -> forward -> D2H frames, per step"}
-    else:
-        # rank 0 owns the clip in pinned host memory: H2D, NCCL scatter of conditioning, render, NCCL gather, D2H
+    # every rank feeds its own pinned host shard through the host-buffer entry point (H2D + forward + D2H + sync per step)
+    for i in range(2):
+        net.forward_host(*host_sets[i % N_INPUT_SETS], out=out_host)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        net.forward_host(*host_sets[i % N_INPUT_SETS], out=out_host)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * B * e2e_steps / (t2.item() * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": d2h * world,
+           "path": "per rank: ap_netg_forward_host (pinned host inputs -> H2D -> forward -> D2H frames -> sync), every step"}
+    if world > 1:
+        # clip-level API: rank 0 owns the clip in pinned host memory: H2D, NCCL scatter of the conditioning tensors,
+        # render per rank, NCCL gather of the frames, D2H on rank 0 (frames.render_frames_sharded)
         T = world * B
         full_host = None
         if rank == 0:
@@ -238,15 +241,14 @@ def main():
         one()
         barrier()
         e0.record()
-        for _ in range(e2e_steps):
+        for _ in range(3):
             one()
         e1.record()
         barrier()
-        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": T * e2e_steps / (t2.item() * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": d2h * world,
-               "path": "rank0 pinned host clip -> H2D -> NCCL scatter -> forward per rank -> NCCL gather -> D2H"}
+        t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        e2e["clip_scatter_gather"] = {"value": T * 3 / (t3.item() * 1e-3), "unit": UNIT,
+                                      "path": "rank0 pinned host clip -> H2D -> NCCL scatter -> forward per rank -> NCCL gather -> D2H"}
 
     # ---------------- per-kernel-class device time (separate profiled pass, CUDA events per launch) ----------------
     peaks = measured_peaks()
