@@ -12,10 +12,10 @@
 // shared-memory instructions instead of 3136 FMAs, and the kernel becomes bound by reading the 64-channel input.
 //
 // Work item = (16x16 output tile, output channel o).  Its 22x22 patch of input positions (reflection applied when
-// the patch is gathered) is 484 GEMM rows = 4 M-tiles of 128.  Warp roles (416 threads):
+// the patch is gathered) is 484 GEMM rows = 4 M-tiles of 128.  Warp roles (672 threads):
 //   warp 0        TMEM allocator, weight loader (bulk copy of the pre-swizzled images), MMA issuer (one lane)
-//   warps 1-8     builders: group g = 0/1 (4 warps each) owns A slot g and builds M-tiles g and g+2 of every item
-//   warps 9-12    epilogue: tcgen05.ld -> t[484][49] in shared memory -> shifted sums -> bias, tanh, store
+//   warps 1-16    builders: group g = 0/1 (8 warps each) owns A slot g and builds M-tiles g and g+2 of every item
+//   warps 17-20   epilogue: tcgen05.ld -> t[484][49] in shared memory -> shifted sums -> bias, tanh, store
 // Two accumulator sets (2 x 256 TMEM columns) let the builders/MMAs of item i+1 run under the epilogue of item i.
 #include "common.cuh"
 #include "umma.cuh"
@@ -33,7 +33,8 @@ constexpr int O_APLANE = 128 * 128;      // [128 rows][64 k] bf16
 constexpr int O_ASLOT = 2 * O_APLANE;    // hi + lo
 constexpr int O_TSTRIDE = 49;            // odd: conflict-free for lane-strided rows
 constexpr int O_TBYTES = ((OPOS * O_TSTRIDE * 4 + 127) / 128) * 128;
-constexpr int O_THREADS = 32 + 256 + 128;
+constexpr int O_BUILD_WARPS = 8;           // builder warps per group (2 groups)
+constexpr int O_THREADS = 32 + 2 * 32 * O_BUILD_WARPS + 128;
 constexpr int O_MAX_ONC = 3;
 constexpr size_t O_SMEM = 1024 + O_MAX_ONC * O_WIMG + 2 * O_ASLOT + O_TBYTES + 512 + 256;
 
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       for (int g = 0; g < 2; ++g) {
-        mbar_init(bars + 8 * g, 128);       // a_full: every builder thread of the group arrives
+        mbar_init(bars + 8 * g, 32 * O_BUILD_WARPS);  // a_full: every builder thread of the group arrives
         mbar_init(bars + 16 + 8 * g, 1);    // a_empty: one tcgen05.commit
         mbar_init(bars + 32 + 8 * g, 1);    // tfull: one tcgen05.commit
         mbar_init(bars + 48 + 8 * g, 4);    // tempty: one arrive per epilogue warp
@@ -129,13 +130,14 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp <= 8) {
+  } else if (warp <= 2 * O_BUILD_WARPS) {
     // ===================== A builders: group g (4 warps) owns slot g =====================
     // A warp builds 32 GEMM rows (= patch positions) of the M-tile.  One load instruction covers two whole rows
     // (lane>>4 picks the row, lane&15 the channel quad): fully coalesced 256-byte reads, and every thread keeps the
     // SAME 4 channels for all its rows, so their mean / rstd live in registers.
-    const int bt = threadIdx.x - 32;        // 0..255
-    const int g = bt >> 7, bw = (bt >> 5) & 3;
+    constexpr int RPW = 128 / O_BUILD_WARPS;  // GEMM rows per builder warp
+    const int bt = threadIdx.x - 32;
+    const int g = bt / (32 * O_BUILD_WARPS), bw = (bt >> 5) % O_BUILD_WARPS;
     const int q = lane & 15, half = lane >> 4;
     int cur_img = -1;
     float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f};
@@ -151,12 +153,12 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
       const float* src_img = p.raw + (size_t)img * 65536 * 64 + 4 * q;
 #pragma unroll 1
       for (int mm = 0; mm < 2; ++mm) {
-        const int row0 = bw * 32 + half;                   // + 2*i: row inside the M-tile
+        const int row0 = bw * RPW + half;                  // + 2*i: row inside the M-tile
         const int pos0 = (g + 2 * mm) * 128 + row0;
         const uint32_t use = (uint32_t)it * 2u + (uint32_t)mm;
-        float4 v[16];
+        float4 v[RPW / 2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < RPW / 2; ++i) {
           const int pos = pos0 + 2 * i;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (pos < OPOS) {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
         }
         mbar_wait(bars + 16 + 8 * g, (use & 1u) ^ 1u);  // the MMAs that read this slot last have retired
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < RPW / 2; ++i) {
           const int row = row0 + 2 * i;
           const float a0 = fmaxf((v[i].x - mean[0]) * rstd[0], 0.f), a1 = fmaxf((v[i].y - mean[1]) * rstd[1], 0.f);
           const float a2 = fmaxf((v[i].z - mean[2]) * rstd[2], 0.f), a3 = fmaxf((v[i].w - mean[3]) * rstd[3], 0.f);
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
       }
     }
   } else {
-    // ===================== epilogue (warps 9..12) =====================
+    // ===================== epilogue (warps 17..20) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int et = (q << 5) | lane;  // a stable 0..127 index (any bijection works for the shifted sums)
     for (int it = 0; it < nitems; ++it) {

@@ -17,9 +17,11 @@
 // fp32-accurate mode runs A_hi*W_hi + A_hi*W_lo + A_lo*W_hi into one TMEM accumulator (NPROD = 3).
 // Two TMEM accumulators (2 x 256 columns) let the epilogue of tile t overlap the MMAs of tile t+1.
 //
-// Warp roles (288 threads): warp 0 = TMEM allocator, weight loader, MMA issuer; warps 1-4 = A builders;
-// warps 5-8 = epilogue (tcgen05.ld -> raw fp32 NHWC store + per-channel sum / sum of squares for the
+// Warp roles (416 threads): warp 0 = TMEM allocator, weight loader, MMA issuer; warps 1-8 = A builders (two groups
+// splitting the K range); warps 9-12 = epilogue (tcgen05.ld -> raw fp32 NHWC store + per-channel sum / sum of squares for the
 // following InstanceNorm, accumulated in registers across the CTA's tiles of one image).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -35,7 +37,7 @@ constexpr int ST_APLANE = 128 * 128;             // one [128 x 64] bf16 A chunk:
 constexpr int ST_ASLOT = 2 * ST_APLANE;          // hi + lo
 constexpr int ST_PW = 70, ST_PH = 8;             // patch: 64+6 columns, 2+6 rows
 constexpr int ST_PATCH = 3 * ST_PH * ST_PW;      // words
-constexpr int ST_THREADS = 288;
+constexpr int ST_THREADS = 32 + 256 + 128;    // MMA warp, 8 builder warps, 4 epilogue warps
 constexpr int ST_EPI = 4 * 2 * 4096;             // two 4 KB staging slabs per epilogue warp
 constexpr int ST_RING = 2 * ST_ASLOT;            // two A slots: chunk c lives in slot c & 1
 constexpr size_t ST_SMEM = 1024 + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4 + 256;
@@ -47,6 +49,7 @@ struct StemP {
   float* out;            // raw NHWC [B,256,256,160]
   double* stats;         // [B][160][2]
   int tiles;             // B * 512 (tile = 2 rows x 64 px)
+  int dbg;               // AP_STEM_DBG timing probe: 1 = no output stores, 2 = no statistics, 4 = builders skip the A build
 };
 
 __device__ __forceinline__ int st_reflect(int i) {
@@ -55,12 +58,12 @@ __device__ __forceinline__ int st_reflect(int i) {
   return i;
 }
 
-template <int C>
+// builds the 16-byte groups [J0, J1) of K-chunk C of one A row
+template <int C, int J0, int J1>
 __device__ __forceinline__ void stem_build_chunk(const uint32_t* __restrict__ pbase, uint8_t* slot, int r8, int atom_off) {
   // groups of 8 consecutive k = 16 bytes of the hi plane and 16 bytes of the lo plane
-  constexpr int NG = (C == 2) ? 4 : 8;
 #pragma unroll
-  for (int j = 0; j < NG; ++j) {
+  for (int j = J0; j < J1; ++j) {
     uint32_t u[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmO) : "memory");
       for (int c = 0; c < 3; ++c) {
-        mbar_init(bars + 8 * c, 128);      // full: every builder thread arrives
+        mbar_init(bars + 8 * c, c == 2 ? 256 : 128);  // full: every builder thread of the chunk arrives
         mbar_init(bars + 24 + 8 * c, 1);   // empty: one tcgen05.commit
       }
       for (int a = 0; a < 2; ++a) {
@@ -170,19 +173,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
         umma_commit(bars + 48 + 8 * acc);
       }
     }
-  } else if (warp <= 4) {
-    // ===================== A builders (128 threads, one A row each) =====================
-    const int row = threadIdx.x - 32;
+  } else if (warp <= 8) {
+    // ===================== A builders (2 groups x 128 threads, one A row per thread) =====================
+    // group 0 builds K-chunk 0 and the first half of chunk 2, group 1 chunk 1 and the second half of chunk 2
+    const int bt = threadIdx.x - 32;
+    const int grp = bt >> 7;
+    const int row = bt & 127;
     const int yy = row >> 6, xx = row & 63;
     const int r8 = row & 7;
     const int atom_off = (row >> 3) * 1024 + r8 * 128;
     const uint32_t* pbase = patch + yy * ST_PW + xx;
-    // per-thread patch elements: idx = row + 128*k, k < 14 (1680 words); (ch, py, px) are tile-independent
-    constexpr int NPRE = (ST_PATCH + 127) / 128;
+    // per-thread patch elements: idx = bt + 256*k, k < 7 (1680 words); (ch, py, px) are tile-independent
+    constexpr int NPRE = (ST_PATCH + 255) / 256;
     int pch[NPRE];  // ch*65536 | py<<8 | px  packed
 #pragma unroll
     for (int k = 0; k < NPRE; ++k) {
-      const int idx = row + 128 * k;
+      const int idx = bt + 256 * k;
       const int ch = idx / (ST_PH * ST_PW);
       const int r = idx - ch * (ST_PH * ST_PW);
       const int py = r / ST_PW, px = r - py * ST_PW;
@@ -204,37 +210,42 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
     };
     if (ntiles > 0) prefetch(t_begin);
     for (int it = 0; it < ntiles; ++it) {
-      if (it > 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the old patch
+      if (it > 0) asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done reading the old patch
 #pragma unroll
       for (int k = 0; k < NPRE; ++k) {
         if (pch[k] >= 0) {
           const float v = pre[k];
           const __nv_bfloat16 h = __float2bfloat16_rn(v);
           const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-          patch[row + 128 * k] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+          patch[bt + 256 * k] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       // the next tile's patch loads fly while this tile's chunks are built
       if (it + 1 < ntiles) prefetch(t_begin + it + 1);
       // chunk c is built in slot c & 1: chunk 0 reuses the slot of the previous tile's chunk 2,
       // chunk 1 the slot of the previous tile's chunk 1, chunk 2 the slot of this tile's chunk 0
       const uint32_t par = ((uint32_t)it & 1u) ^ 1u;
-      mbar_wait(bars + 24 + 16, par);
-      stem_build_chunk<0>(pbase, gA, r8, atom_off);
-      fence_proxy_async();
-      mbar_arrive(bars + 0);
-      mbar_wait(bars + 24 + 8, par);
-      stem_build_chunk<1>(pbase, gA + ST_ASLOT, r8, atom_off);
-      fence_proxy_async();
-      mbar_arrive(bars + 8);
-      mbar_wait(bars + 24 + 0, (uint32_t)it & 1u);
-      stem_build_chunk<2>(pbase, gA, r8, atom_off);
+      if (grp == 0) {
+        mbar_wait(bars + 24 + 16, par);
+        if (!(p.dbg & 4)) stem_build_chunk<0, 0, 8>(pbase, gA, r8, atom_off);
+        fence_proxy_async();
+        mbar_arrive(bars + 0);
+        mbar_wait(bars + 24 + 0, (uint32_t)it & 1u);
+        if (!(p.dbg & 4)) stem_build_chunk<2, 0, 2>(pbase, gA, r8, atom_off);
+      } else {
+        mbar_wait(bars + 24 + 8, par);
+        if (!(p.dbg & 4)) stem_build_chunk<1, 0, 8>(pbase, gA + ST_ASLOT, r8, atom_off);
+        fence_proxy_async();
+        mbar_arrive(bars + 8);
+        mbar_wait(bars + 24 + 0, (uint32_t)it & 1u);
+        if (!(p.dbg & 4)) stem_build_chunk<2, 2, 4>(pbase, gA, r8, atom_off);
+      }
       fence_proxy_async();
       mbar_arrive(bars + 16);
     }
   } else {
-    // ===================== epilogue (warps 5..8) =====================
+    // ===================== epilogue (warps 9..12) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row0 = q * 32;
     const int yy = row0 >> 6, xx0 = row0 & 63;
@@ -256,12 +267,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + (uint32_t)(acc * 256 + g * 32), v);
         const uint32_t sl = (blk & 1u) * 4096;
-        epi_store_block<1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, g * 32, x0 + xx0, y0 + yy, img);
-        float sq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-        ssum[g] += butterfly_colsum(v, lane);
-        ssq[g] += butterfly_colsum(sq, lane);
+        if (!(p.dbg & 1)) epi_store_block<1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO, g * 32, x0 + xx0, y0 + yy, img);
+        if (p.dbg & 2) continue;
+        float cs, cq;
+        slab_colsums(slab_gen + sl, lane, &cs, &cq);
+        ssum[g] += cs;
+        ssq[g] += cq;
       }
       tc_fence_before();
       __syncwarp();
@@ -332,6 +343,11 @@ int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* s
   StemP p{};
   AP_TRY(tmap_encode_out(&p.tmO, out, B, 256, 256, ST_N, 1, 0, 0));
   p.in = in; p.wimg = wimg; p.out = out; p.stats = stats; p.tiles = B * 512;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("AP_STEM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   const int grid = p.tiles < g_stem_sms ? p.tiles : g_stem_sms;
   if (nprod == 3)
     stem_umma_kernel<3><<<grid, ST_THREADS, ST_SMEM, st>>>(p);

@@ -314,11 +314,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
         epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[0], p.out_coff + w.n0 + c0, ox, oy, w.img, opol);
         if (strow != nullptr) {
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          const float cs = butterfly_colsum(v, lane);
-          const float cq = butterfly_colsum(sq, lane);
+          float cs, cq;
+          slab_colsums(slab_gen + sl, lane, &cs, &cq);
           if (acc_item) {
             sacc[c0 + lane] += cs;
             sacc[STAT_ACC_COLS + c0 + lane] += cq;
@@ -582,11 +579,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         if (!AP_DBG(p.dbg & 2))
           epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[phs], p.out_coff + ch, ox, oy, w.img, opol);
         if (strow != nullptr && !AP_DBG(p.dbg & 4)) {
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          const float cs = butterfly_colsum(v, lane);
-          const float cq = butterfly_colsum(sq, lane);
+          float cs, cq;
+          slab_colsums(slab_gen + sl, lane, &cs, &cq);
           if (acc_item) {  // the phases of a packed transposed conv fold onto the same channel
             sacc[ch + lane] += cs;
             sacc[STAT_ACC_COLS + ch + lane] += cq;

@@ -231,4 +231,21 @@ static __device__ __forceinline__ void epi_store_block(const float (&v)[32], uin
   }
 }
 
+// Column sums of the 32 x 32 fp32 block an epilogue warp has just staged with epi_store_block (128B-swizzled rows):
+// lane L reads column L of every row -- 32 conflict-free shared-memory loads (one row = 32 banks) instead of two
+// 31-shuffle butterflies.  The TMA store of the same slab only reads it, so the two overlap.
+static __device__ __forceinline__ void slab_colsums(const uint8_t* slab_gen, int lane, float* sum, float* sumsq) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll
+  for (int r = 0; r < 32; r += 2) {
+    const float a = *reinterpret_cast<const float*>(slab_gen + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+    const float b = *reinterpret_cast<const float*>(slab_gen + (r + 1) * 128 + ((chunk ^ ((r + 1) & 7)) << 4) + within);
+    s0 += a; q0 = fmaf(a, a, q0);
+    s1 += b; q1 = fmaf(b, b, q1);
+  }
+  *sum = s0 + s1;
+  *sumsq = q0 + q1;
+}
+
 }  // namespace ap
