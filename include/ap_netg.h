@@ -75,6 +75,17 @@ int ap_netg_forward_host(ap_netg* handle, int B, const float* input, const float
                          const float* land2, const float* motion, const float* flow, const float* ifmask,
                          float* out, void* cuda_stream);
 
+/* Output stage after netG, one fused elementwise kernel (device pointers, asynchronous on `cuda_stream`).
+ * Replaces: the foreground/background blend of GeomCGTIFWTestModel.forward
+ *   mask1 = F.grid_sample(mask, warp_motion, align_corners=True); fake_B = ((fake_B/2+0.5)*mask1 +
+ *   (fakeB_static/2+0.5)*(1-mask1))*2-1          (Module2/models/geomcgt_ifw_test_model.py:297-300)
+ * and util.tensor2im, ((x+1)/2*255).astype(uint8) as HWC RGB with grayscale tiled to 3 channels
+ * (Module2/util/util.py:9-29; call site Module2/util/visualizer.py:16-52 via Module2/test.py:63-65).
+ *   fake_B [B,onc,256,256]; mask [B,1,256,256], motion [B,256,256,2], static_B [B,onc,256,256] -- all three or none
+ *   (none: no blend, conversion only); blended [B,onc,256,256] fp32 and/or image_u8 [B,256,256,3], either may be NULL. */
+int ap_netg_compose(int device, int B, int output_nc, const float* fake_B, const float* mask, const float* motion,
+                    const float* static_B, float* blended, uint8_t* image_u8, void* cuda_stream);
+
 /* Number of kernels of this library launched by the most recent forward on this handle. */
 int ap_netg_last_launch_count(ap_netg* handle, int64_t* count);
 

@@ -342,6 +342,38 @@ def double_feature_warping_closed_form(x, motion, flow, ifmask, level):
     return torch.cat([x1, x2], 1)
 
 
+# --------------------------------------------------------------------------------------
+# output stage after netG ("next" rows f1 / f4): blend with the static drawing and uint8 conversion
+# --------------------------------------------------------------------------------------
+def blend_foreground(fake_B, mask, warp_motion, fakeB_static):
+    """GeomCGTIFWTestModel.forward, Module2/models/geomcgt_ifw_test_model.py:297-300."""
+    mask1 = F.grid_sample(mask, warp_motion, align_corners=True)
+    return ((fake_B / 2 + 0.5) * mask1 + (fakeB_static / 2 + 0.5) * (1 - mask1)) * 2 - 1
+
+
+def tensor2im_batch(x: torch.Tensor):
+    """util.tensor2im (Module2/util/util.py:9-29) applied to every frame of a batch: uint8 [B,H,W,3]."""
+    import numpy as np
+    arr = x.detach().cpu().float().numpy()
+    if arr.shape[1] == 1:  # grayscale to RGB
+        arr = np.tile(arr, (1, 3, 1, 1))
+    img = (np.transpose(arr, (0, 2, 3, 1)) + 1) / 2.0 * 255.0
+    return img.astype(np.uint8)
+
+
+def make_compose_inputs(B: int, onc: int, seed: int):
+    """Seeded stand-ins for (fake_B, mask, warp_motion, fakeB_static): a tanh-range frame, a binary matte
+    ((matte > 0.5).float(), geomcgt_ifw_test_model.py:280), the smooth motion grid of make_inputs, a static drawing."""
+    g = torch.Generator().manual_seed(seed)
+    fake = torch.tanh(_smooth_field(B, onc, 256, 16, 1.5, g))
+    stat = torch.tanh(_smooth_field(B, onc, 256, 32, 1.5, g))
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, 256), torch.linspace(-1, 1, 256), indexing="ij")
+    cx, cy = 0.1 * torch.randn(B, 1, 1, generator=g), 0.1 * torch.randn(B, 1, 1, generator=g)
+    mask = ((((xs[None] - cx) / 0.6) ** 2 + ((ys[None] - cy) / 0.8) ** 2) < 1.0).float()[:, None]
+    motion = make_inputs(B, seed=seed + 1, kind="smooth")[3]
+    return fake, mask, motion, stat
+
+
 def flops_per_frame(output_nc: int = 1) -> float:
     """2*MACs of the 38 Conv2d + 2 ConvTranspose2d calls per frame: 140.125e9 / 140.947e9."""
     total = 0.0
