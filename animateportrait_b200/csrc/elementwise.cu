@@ -320,6 +320,8 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpP p) {
   Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, S, S, 0};
 #pragma unroll 1
   for (int lp = py; lp < WARP_PIX; lp += NY) {
+    // All 8 gathers are issued back to back, unconditionally: a tap outside the image reads pixel 0 with weight 0
+    // (bilinear 'zeros' padding).  With the loads under `if (off >= 0)` every one of them was waited for in turn.
     float4 val[2][4];
     float wt[2][4];
 #pragma unroll
@@ -327,23 +329,21 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpP p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int off = s_off[kind][k][lp];
-        wt[kind][k] = s_w[kind][k][lp];
-        val[kind][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (off >= 0) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)off * p.raw_C));
-          v.x = fmaxf((v.x - mean[0]) * rstd[0], 0.f); v.y = fmaxf((v.y - mean[1]) * rstd[1], 0.f);
-          v.z = fmaxf((v.z - mean[2]) * rstd[2], 0.f); v.w = fmaxf((v.w - mean[3]) * rstd[3], 0.f);
-          val[kind][k] = v;
-        }
+        wt[kind][k] = (off >= 0) ? s_w[kind][k][lp] : 0.f;
+        val[kind][k] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(off >= 0 ? off : 0) * p.raw_C));
       }
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      a.x = fmaf(val[0][k].x, wt[0][k], a.x); a.y = fmaf(val[0][k].y, wt[0][k], a.y);
-      a.z = fmaf(val[0][k].z, wt[0][k], a.z); a.w = fmaf(val[0][k].w, wt[0][k], a.w);
-      b.x = fmaf(val[1][k].x, wt[1][k], b.x); b.y = fmaf(val[1][k].y, wt[1][k], b.y);
-      b.z = fmaf(val[1][k].z, wt[1][k], b.z); b.w = fmaf(val[1][k].w, wt[1][k], b.w);
-    }
+    for (int kind = 0; kind < 2; ++kind)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float4 v = val[kind][k];
+        v.x = fmaxf((v.x - mean[0]) * rstd[0], 0.f); v.y = fmaxf((v.y - mean[1]) * rstd[1], 0.f);
+        v.z = fmaxf((v.z - mean[2]) * rstd[2], 0.f); v.w = fmaxf((v.w - mean[3]) * rstd[3], 0.f);
+        float4& acc = kind == 0 ? a : b;
+        acc.x = fmaf(v.x, wt[kind][k], acc.x); acc.y = fmaf(v.y, wt[kind][k], acc.y);
+        acc.z = fmaf(v.z, wt[kind][k], acc.z); acc.w = fmaf(v.w, wt[kind][k], acc.w);
+      }
     if (!s_keep[lp]) b = make_float4(-1.f, -1.f, -1.f, -1.f);
     const int pix = pix_base + lp;
     const int i = pix >> logS, j = pix & (S - 1);
