@@ -34,9 +34,9 @@ if has list; then
   echo "ncu list rc=$?"
 fi
 if has full; then
-  # one whole forward (71 launches) with the full metric set; the .ncu-rep is reduced to CSV on the box because
+  # one whole forward (66 launches) with the full metric set; the .ncu-rep is reduced to CSV on the box because
   # gpurun only brings back 64 MiB
-  timeout 1200 ncu --set full --clock-control none --launch-skip 300 --launch-count 71 \
+  timeout 1200 ncu --set full --clock-control none --launch-skip 300 --launch-count 66 \
     -o /tmp/${TAG}_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_full.log 2>&1
   echo "ncu full rc=$?"
   ncu -i /tmp/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
