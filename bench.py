@@ -292,7 +292,7 @@ def main():
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            fps, iters, cores = time_oracle(4, onc, 12.0, 8)
+            fps, iters, cores = time_oracle(4, onc, 12.0, 40)  # ~12 s of CPU work on all host cores
             import torch as _t
             cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{iters} forwards of a 4-frame sample of the batch, oracle port of the reference "
