@@ -35,6 +35,15 @@ void set_error(const char* fmt, ...);
     }                               \
   } while (0)
 
+// Device-side per-image dependency flags ("flag sync") for the conv -> InstanceNorm apply -> conv chain of the trunk.
+// A producer kernel adds to done[img] as its work on image img lands in memory; the consumer spins (acquire) until the
+// count reaches `expected` before touching that image.  The apply pass then runs on a side stream UNDER the conv that
+// feeds it, image by image, instead of after it (InstanceNorm needs whole planes, not whole batches).
+struct FlagWait {
+  const uint32_t* flags;  // [B], or null
+  uint32_t expected;
+};
+
 // Activation formats in HBM. All activations are NHWC; `pad` is a halo of that many pixels on each
 // side of H and W that the PRODUCER fills (reflection) or leaves zero.
 enum ActFmt : int {
@@ -118,6 +127,9 @@ struct ApplyP {
   // destination (may be absent: fmt = -1)
   int fmt; void* d0; void* d1; int dC, dcoff, dpad;
   int halo_reflect;  // fill the halo ring by reflection (pad==1)
+  // flag sync (trunk only; C = 256): wait for up to two producers per image, signal own completion per image
+  FlagWait wait0, wait1;
+  uint32_t* done_flags;
   int l2_hints;      // raw loads evict_first (set by launch_apply from AP_NETG_L2_HINTS bit 1)
 };
 
@@ -161,9 +173,27 @@ __device__ __forceinline__ void stats_to_affine(const double* st, int n, int sta
 }
 #endif
 
+#ifdef __CUDACC__
+__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t expected) {
+  uint32_t v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= expected) break;
+    __nanosleep(128);
+    if (++spins > (1u << 21)) __trap();  // ~0.3 s: a lost dependency must fail the launch, never hang the GPU
+  }
+}
+__device__ __forceinline__ void flag_add(uint32_t* flag, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+#endif
+
 // ---- launchers (each returns AP_OK / error and counts one launch) ----
 int launch_conv_simt(const SimtConvP& p, cudaStream_t st);
 int launch_apply(const ApplyP& p, cudaStream_t st);
+int launch_apply_flags(const ApplyP& p, cudaStream_t st);  // persistent, per-image flag sync (C = 256)
+uint32_t apply_flags_done_per_image(int H, int W);
+int apply_flags_regs_per_cta();
 int launch_warp(const WarpP& p, cudaStream_t st);
 int launch_out_conv(const OutConvP& p, cudaStream_t st);
 int launch_read(const ReadP& p, cudaStream_t st);
@@ -185,7 +215,10 @@ struct UmmaConv;  // opaque launch record (tensor maps + params), see conv_umma.
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff,
                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int nprod,
                      float* out_raw, int out_C, int out_coff, double* stats, int stat_C, int stat_coff,
-                     const PhasePack* pk = nullptr);
+                     const PhasePack* pk = nullptr, FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done_flags = nullptr);
+uint32_t umma_conv_done_per_image(const UmmaConv* c);
+bool umma_pairs_available();  // CTA-pair kernels enabled and launchable on this device
+int umma_pair_regs_per_cta(); // registers one CTA of the trunk pair kernel occupies  // what done_flags[img] reaches when image img is complete
 void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
 int umma_init();  // resolves cuTensorMapEncodeTiled, sets func attributes

@@ -55,6 +55,8 @@ struct alignas(64) UmmaParams {
   // n_full whole groups with bn = Cout, then (groups - n_full) * split N-parts
   int n_full, split, n_items;
   int l2_hints;  // bit 0: raw output stores evict_last (AP_NETG_L2_HINTS)
+  FlagWait wait;         // pair kernel: per-image readiness of the input activations (flag sync), or {null, 0}
+  uint32_t* done_flags;  // pair kernel: += 32-column blocks finished per image, or null
   int dbg;  // timing diagnostics only (AP_UMMA_DBG): 1 = no TMA loads after the first fill, 2 = no output stores, 4 = no statistics
 };
 
@@ -433,10 +435,18 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     if (lane == 0) {
       const uint32_t full0 = (CG == 2) ? mapa_rank(bars, 0) : bars;  // full barriers live in the leader
       uint32_t cnt = 0;
+      int ready_img = -1;
       for (int li = 0;; ++li) {
         const int item = item_at<ACC>(p, li, unit, nunits, Krun);
         if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, rank);
+        if (p.wait.flags != nullptr && w.img != ready_img) {
+          // the apply pass that produces this image's operands runs concurrently (flag sync): wait for it, then make
+          // its generic-proxy writes visible to the TMA loads below
+          flag_wait(p.wait.flags + w.img, p.wait.expected);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          ready_img = w.img;
+        }
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
         const int wrows = w.bn / CG;
         const int nbox = wrows / Cfg::W_BOX;
@@ -597,6 +607,17 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * acc);
         else mbar_arrive(bars + 144 + 8 * acc);
       }
+      if (p.done_flags != nullptr) {
+        // this warp's share of the item (bn/32 column blocks of 32 rows) has landed: stores complete, statistics added
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_wait<0>();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          __threadfence();
+          flag_add(p.done_flags + w.img, (uint32_t)(w.bn >> 5));
+        }
+      }
     }
     if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
@@ -730,7 +751,7 @@ static int max_pairs(int BN, int nprod) {
 // out-of-bounds with zeros); reflect-padded ones address the haloed buffer (halo = in.pad >= conv pad).
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
                      const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, double* stats,
-                     int stat_C, int stat_coff, const PhasePack* pk) {
+                     int stat_C, int stat_coff, const PhasePack* pk, FlagWait wait, uint32_t* done_flags) {
   AP_TRY(umma_init());
   AP_REQUIRE(in.fmt == FMT_BF16X2 || in.fmt == FMT_BF16, AP_ERR_INVALID, "umma conv needs bf16 activations");
   AP_REQUIRE(nprod == 1 || (nprod == 3 && in.fmt == FMT_BF16X2 && w_lo), AP_ERR_INVALID, "umma conv: nprod/format");
@@ -819,6 +840,10 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   p.split = split;
   p.dbg = g_dbg;
   p.l2_hints = g_l2_hints;
+  AP_REQUIRE((wait.flags == nullptr && done_flags == nullptr) || (c->cg == 2 && !pk), AP_ERR_UNSUPPORTED,
+             "flag sync is implemented in the (unpacked) CTA-pair kernel only");
+  p.wait = wait;
+  p.done_flags = done_flags;
   p.n_full = groups - rem;
   p.n_items = p.n_full + rem * split;
   c->grid = dim3((unsigned)((p.n_items < G ? p.n_items : G) * c->cg), 1);
@@ -826,7 +851,20 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   return AP_OK;
 }
 
+bool umma_pairs_available() { return umma_init() == AP_OK && g_pair != 0 && max_pairs(256, 3) > 0; }
+
+int umma_pair_regs_per_cta() {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, (const void*)conv_umma_kernel<256, 3, 2, false>) != cudaSuccess) return 1 << 30;
+  return ((a.numRegs + 7) / 8 * 8) * 32 * ((192 / 32 + 3) / 4 * 4);
+}
+
 void umma_conv_destroy(UmmaConv* c) { delete c; }
+
+// every epilogue warp (4 per CTA) adds bn/32 per item: per image = tiles * 4 * BN/32
+uint32_t umma_conv_done_per_image(const UmmaConv* c) {
+  return (uint32_t)(c->p.tiles_x * c->p.tiles_y) * 4u * (uint32_t)(c->BN / 32);
+}
 
 template <int BN, int NPROD, int CG>
 static int launch_one(const UmmaConv* c, cudaStream_t st) {

@@ -156,8 +156,162 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Flag-synchronised apply for the 256-channel trunk (see FlagWait in common.cuh).  Persistent: one 256-thread CTA per
+// SM walks (image, 32-pixel chunk) items in image order; before the first item of an image it waits until the conv(s)
+// that produce the image have signalled completion, after every item it signals its own.  It is launched on a side
+// stream and runs UNDER the conv kernel that feeds it.  Progress argument: the consumer conv may occupy every SM and
+// spin on this kernel's flags before this kernel's CTAs are placed, so ONE CTA of this kernel must always fit next to
+// a resident conv CTA: no shared memory, 256 threads x <= 72 registers (18 K of the 64 K registers; a 192-thread conv
+// CTA takes up to 31 K with the 4-warp allocation granularity).  apply_flags_fits() checks it against the compiled
+// kernels; with 512-thread CTAs (37 K) the pair did not fit and the forward dead-locked intermittently.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_coherent(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+constexpr int AF_THREADS = 256, AF_TPP = 64, AF_NY = AF_THREADS / AF_TPP, AF_PIX = 8 * AF_NY;
+
+template <int MODE>
+__global__ void __maxnreg__(72) apply_flags_kernel(const ApplyP p) {
+  const int cq = threadIdx.x % AF_TPP, py = threadIdx.x / AF_TPP;
+  const int c = cq * 4;
+  const int HW = p.H * p.W;
+  const int logW = 31 - __clz(p.W);
+  const int items_per_img = HW / AF_PIX;
+  const int total = items_per_img * p.B;
+  Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
+  float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur = -1;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int n = item / items_per_img;
+    const int pix0 = (item - n * items_per_img) * AF_PIX + py;
+    if (n != cur) {
+      if (threadIdx.x == 0) {
+        if (p.wait0.flags) flag_wait(p.wait0.flags + n, p.wait0.expected);
+        if (p.wait1.flags) flag_wait(p.wait1.flags + n, p.wait1.expected);
+      }
+      __syncthreads();
+      const double inv_n = 1.0 / (double)HW;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
+        else { mean[e] = p.bias ? -p.bias[c + e] : 0.f; rstd[e] = 1.f; }
+        if (MODE == 1) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
+      }
+      cur = n;
+    }
+    const float* raw = p.raw + ((size_t)n * HW) * p.raw_C + p.raw_coff + c;
+    const float* raw2 = (MODE == 1) ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
+    const float* rin = (MODE == 2) ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
+    float* rout = p.res_out ? p.res_out + ((size_t)n * HW) * p.C + c : nullptr;
+#pragma unroll 1
+    for (int k0 = 0; k0 < AF_PIX; k0 += 4 * AF_NY) {
+      float4 v[4], u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pix = pix0 + k0 + j * AF_NY;
+        v[j] = ld_coherent(raw + (size_t)pix * p.raw_C);
+        if (MODE == 1) u[j] = ld_coherent(raw2 + (size_t)pix * p.raw2_C);
+        if (MODE == 2) u[j] = ld_coherent(rin + (size_t)pix * p.C);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pix = pix0 + k0 + j * AF_NY;
+        float4 o;
+        o.x = (v[j].x - mean[0]) * rstd[0];
+        o.y = (v[j].y - mean[1]) * rstd[1];
+        o.z = (v[j].z - mean[2]) * rstd[2];
+        o.w = (v[j].w - mean[3]) * rstd[3];
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (MODE == 1) {
+          o.x += (u[j].x - mean2[0]) * rstd2[0];
+          o.y += (u[j].y - mean2[1]) * rstd2[1];
+          o.z += (u[j].z - mean2[2]) * rstd2[2];
+          o.w += (u[j].w - mean2[3]) * rstd2[3];
+        }
+        if (MODE == 2) { o.x += u[j].x; o.y += u[j].y; o.z += u[j].z; o.w += u[j].w; }
+        if (rout) *reinterpret_cast<float4*>(rout + (size_t)pix * p.C) = o;
+        if (p.fmt >= 0) store_pixel(d, n, pix >> logW, pix & (p.W - 1), c, o);
+      }
+    }
+    if (p.done_flags) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) flag_add(p.done_flags + n, 1u);
+    }
+  }
+}
+
+uint32_t apply_flags_done_per_image(int H, int W) { return (uint32_t)(H * W / AF_PIX); }
+
+// registers one CTA of the flag apply kernel occupies (4-warp allocation granularity, 8-register rounding)
+int apply_flags_regs_per_cta() {
+  int worst = 0;
+  cudaFuncAttributes a;
+  const void* ks[3] = {(const void*)apply_flags_kernel<0>, (const void*)apply_flags_kernel<1>, (const void*)apply_flags_kernel<2>};
+  for (const void* k : ks) {
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) return 1 << 30;
+    const int r = ((a.numRegs + 7) / 8 * 8) * 32 * ((AF_THREADS / 32 + 3) / 4 * 4);
+    worst = r > worst ? r : worst;
+  }
+  return worst;
+}
+
+static int g_af_sms = 0;
+
+int launch_apply_flags(const ApplyP& p, cudaStream_t st) {
+  AP_REQUIRE(p.C == 256 && p.raw_C % 4 == 0 && p.raw_coff % 4 == 0, AP_ERR_INVALID, "apply_flags: C=%d", p.C);
+  AP_REQUIRE(p.fmt < 0 || (p.dC % 4 == 0 && p.dcoff % 4 == 0), AP_ERR_INVALID, "apply_flags: dst channel layout");
+  AP_REQUIRE((p.W & (p.W - 1)) == 0 && (p.H * p.W) % AF_PIX == 0 && p.res_fmt < 0, AP_ERR_INVALID, "apply_flags: %dx%d", p.H, p.W);
+  AP_REQUIRE(!(p.raw2 && p.res_in), AP_ERR_INVALID, "apply_flags: shortcut operand and residual stream are exclusive");
+  if (g_af_sms == 0) {
+    int dev = 0;
+    AP_CUDA(cudaGetDevice(&dev));
+    AP_CUDA(cudaDeviceGetAttribute(&g_af_sms, cudaDevAttrMultiProcessorCount, dev));
+    // must be co-resident with conv CTAs that configure the SM for (almost) all-shared-memory: ask for the same
+    // carve-out, an SM has one L1/shared split at a time
+    AP_CUDA(cudaFuncSetAttribute(apply_flags_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    AP_CUDA(cudaFuncSetAttribute(apply_flags_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    AP_CUDA(cudaFuncSetAttribute(apply_flags_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  const int total = p.H * p.W / AF_PIX * p.B;
+  const int grid = total < g_af_sms ? total : g_af_sms;
+  if (p.raw2) apply_flags_kernel<1><<<grid, AF_THREADS, 0, st>>>(p);
+  else if (p.res_in) apply_flags_kernel<2><<<grid, AF_THREADS, 0, st>>>(p);
+  else apply_flags_kernel<0><<<grid, AF_THREADS, 0, st>>>(p);
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  return AP_OK;
+}
+
+// An SM has ONE L1 / shared-memory split at a time.  The persistent convs configure it for (almost) all shared memory;
+// a kernel that prefers another split may not become co-resident with them.  The flag-synchronised apply kernel MUST be
+// co-resident and always asks for the max-shared carve-out; for the ordinary side-stream kernels it is an option.
+bool carveout_enabled() {  // AP_NETG_CARVEOUT=1 (A/B): measured 1-2 % SLOWER overall -- the elementwise kernels lose their L1
+  static int v = -1;      // and the side-stream kernels overlap the convs about as well without it -- so it is off by default
+  if (v < 0) { const char* e = getenv("AP_NETG_CARVEOUT"); v = (e && e[0] == '1'); }
+  return v != 0;
+}
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  if (carveout_enabled()) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+template <int TPP>
+static void apply_carveouts() {
+  prefer_max_shared(apply_kernel<TPP, 0>);
+  prefer_max_shared(apply_kernel<TPP, 1>);
+  prefer_max_shared(apply_kernel<TPP, 2>);
+  prefer_max_shared(apply_kernel<TPP, 3>);
+}
+
 template <int TPP>
 static void launch_apply_tpp(const ApplyP& p, dim3 grid, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { apply_carveouts<TPP>(); once = true; }
   if (p.raw2) apply_kernel<TPP, 1><<<grid, 256, 0, st>>>(p);
   else if (p.res_in) apply_kernel<TPP, 2><<<grid, 256, 0, st>>>(p);
   else if (p.res_fmt >= 0) apply_kernel<TPP, 3><<<grid, 256, 0, st>>>(p);
@@ -356,6 +510,13 @@ int launch_warp(const WarpP& p, cudaStream_t st) {
   AP_REQUIRE(p.C == 32 || p.C == 64 || p.C == 128, AP_ERR_INVALID, "warp: C=%d", p.C);
   AP_REQUIRE((p.S & (p.S - 1)) == 0 && (p.S * p.S) % WARP_PIX == 0, AP_ERR_INVALID, "warp: S=%d", p.S);
   dim3 grid(p.S * p.S / WARP_PIX, p.B);
+  static bool once = false;
+  if (!once) {
+    prefer_max_shared(warp_kernel<8>);
+    prefer_max_shared(warp_kernel<16>);
+    prefer_max_shared(warp_kernel<32>);
+    once = true;
+  }
   if (p.C == 32) warp_kernel<8><<<grid, 256, 0, st>>>(p);
   else if (p.C == 64) warp_kernel<16><<<grid, 256, 0, st>>>(p);
   else warp_kernel<32><<<grid, 256, 0, st>>>(p);

@@ -14,6 +14,7 @@
 namespace ap {
 
 void launches_add(int n);
+bool carveout_enabled();
 
 // The weights travel BY VALUE in the kernel parameters ([9][CIN][COUT] fp32, at most 9 KB): with the tap /
 // channel loops fully unrolled every FMA reads its weight straight from the constant bank, no load at all.
@@ -116,6 +117,13 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
 int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
                            const Raw& r0, const Raw& r1, const Raw& r2, int B, cudaStream_t st) {
   AP_REQUIRE(r0.B == 2 * B && r1.B == 2 * B && r2.B == 2 * B, AP_ERR_INVALID, "landmark: workspace batch");
+  static bool once = false;
+  if (!once && carveout_enabled()) {  // co-residency with the stem kernel's all-shared-memory SM configuration (see elementwise.cu)
+    cudaFuncSetAttribute(land_conv_kernel<1, 8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(land_conv_kernel<8, 16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(land_conv_kernel<16, 16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    once = true;
+  }
   {
     LandP<1, 8> a{land1, land2, nullptr, r0.p, r0.stats, B, 256, 256, {}};
     memcpy(a.w, w0, sizeof(a.w));

@@ -168,6 +168,7 @@ struct ap_netg {
   bool profiling = false;
   bool overlap = true;  // run independent branches on side streams (AP_NETG_OVERLAP=0 turns it off)
   bool out_umma = true; // tcgen05 output stage (AP_NETG_OUT_UMMA=0: CUDA-core kernel)
+  bool flagsync = false;     // trunk: apply passes run under the convs, per-image device flags (AP_NETG_FLAGSYNC=1: on)
   bool convt_packed = true;  // transposed convs as one phase-packed N=256 conv (AP_NETG_CONVT_PACKED=0: four phase convs)
   std::vector<cudaEvent_t> ev;      // ev[0] = start, ev[i+1] = after launch i
   std::vector<int> ev_class;        // class of launch i
@@ -253,6 +254,9 @@ struct Runner {
     soff += n * sizeof(double);
     return p;
   }
+  // per-image dependency counters live in the statistics arena: zeroed at the start of every forward
+  uint32_t* alloc_flags() { return reinterpret_cast<uint32_t*>(alloc_stats((size_t)(pl->B + 1) / 2)); }
+  bool flag_mode() const { return h->flagsync && h->prec == AP_PREC_FP32X3; }
   Act act(int B, int H, int W, int C, int pad, int fmt) {
     Act a;
     a.B = B; a.H = H; a.W = W; a.C = C; a.pad = pad; a.fmt = fmt;
@@ -302,7 +306,8 @@ struct Runner {
   }
 
   // A 3x3 / transposed-conv layer on the tensor-core or the CUDA-core path, by handle precision.
-  int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff) {
+  int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff,
+           FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done = nullptr) {
     if (h->prec == AP_PREC_FP32_SIMT) {
       if (ph != PH_EXEC) return AP_OK;
       SimtConvP p{};
@@ -318,7 +323,7 @@ struct Runner {
     if (ph == PH_BUILD) {
       UmmaConv* c = nullptr;
       AP_TRY(umma_conv_create(&c, g, in, in_coff, w.hi, w.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C,
-                              out_coff, out.stats, out.C, out_coff));
+                              out_coff, out.stats, out.C, out_coff, nullptr, wait, done));
       pl->convs.push_back(c);
       return AP_OK;
     }
@@ -360,7 +365,8 @@ struct Runner {
     return mark(g.taps.n == 49 ? CL_STEM : CL_LAND, conv_flops(g));
   }
   int apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias = nullptr,
-            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr, const Act* res_act = nullptr) {
+            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr, const Act* res_act = nullptr,
+            FlagWait fl_w0 = FlagWait{nullptr, 0}, FlagWait fl_w1 = FlagWait{nullptr, 0}, uint32_t* fl_done = nullptr) {
     if (ph != PH_EXEC) return AP_OK;
     ApplyP p{};
     p.raw = r.p; p.raw_C = r.C; p.raw_coff = rcoff;
@@ -375,7 +381,12 @@ struct Runner {
     if (dst) { p.fmt = dst->fmt; p.d0 = dst->p0; p.d1 = dst->p1; p.dC = dst->C; p.dcoff = dcoff; p.dpad = dst->pad; }
     else p.fmt = -1;
     p.halo_reflect = halo;
-    AP_TRY(launch_apply(p, st));
+    if (fl_done != nullptr || fl_w0.flags != nullptr) {
+      p.wait0 = fl_w0; p.wait1 = fl_w1; p.done_flags = fl_done;
+      AP_TRY(launch_apply_flags(p, st));
+    } else {
+      AP_TRY(launch_apply(p, st));
+    }
     return mark(CL_APPLY, 0.0);
   }
   int warp(const Raw& r, int rcoff, int C, int level, const Inputs& in, const Act& dst, int dcoff) {
@@ -540,16 +551,32 @@ int Runner::run(const Inputs& in) {
   AP_TRY(order_after(main_st, s1));
   AP_TRY(order_after(main_st, s2));
 
-  // ---- merge: Conv3 768->256, zero pad, bias kept, no norm (networks.py:1251,1330) ----
+  // ---- merge + 9 residual blocks (networks.py:1251,1330,1333-1337, 2303-2421) ----
+  // Flag mode (fp32-accurate tensor-core path): all convs go back to back on the caller's stream, all InstanceNorm
+  // apply passes on ONE side stream; they are ordered per image by device-side counters, so an apply pass runs under
+  // the conv that feeds it and the next conv starts on images that are already applied.  Otherwise: stream order, the
+  // shortcut conv of a ResnetBlock2 on a side stream under conv1's apply.
+  const bool fm = flag_mode();
+  const uint32_t conv_n = (uint32_t)(64 * 64 / 128) * 4u * (256u / 32u);  // == umma_conv_done_per_image of a 64x64, N=256 conv
+  const uint32_t apply_n = apply_flags_done_per_image(64, 64);
+  cudaStream_t sA = fm ? s1 : main_st;
+  if (fm) AP_TRY(order_after(sA, main_st));
+  auto FW = [&](uint32_t* f, uint32_t n) { return FlagWait{f, n}; };
+  const FlagWait none{nullptr, 0};
+
   Raw rM = raw(B, 64, 64, 256, false);
-  AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0));
-  AP_TRY(apply(rM, 0, 256, 0, &Xb[0], 0, 1, h->b_merge, nullptr, nullptr, xres[0]));
+  uint32_t* fM = fm ? alloc_flags() : nullptr;
+  uint32_t* a_prev = fm ? alloc_flags() : nullptr;   // "the block input is applied" counter of the previous stage
+  AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0, none, fM));
+  on(sA);
+  AP_TRY(apply(rM, 0, 256, 0, &Xb[0], 0, 1, h->b_merge, nullptr, nullptr, xres[0], nullptr, fm ? FW(fM, conv_n) : none, none, a_prev));
+  on(main_st);
   if (res_from_act) tap_act("merge", Xb[0], 0, 256);
   else tap_f32("merge", xres[0], B, 64, 64, 256);
 
   AP_TRY(order_after(main_st, s3));
+  if (fm) AP_TRY(order_after(sA, s3));   // the landmark channels of the 288-channel block inputs
 
-  // ---- 9 residual blocks (networks.py:1333-1337, 2303-2421) ----
   for (int i = 0; i < 9; ++i) {
     const std::string b = "model2." + std::to_string(i);
     const bool b2 = (i % 3) == 0;
@@ -557,29 +584,40 @@ int Runner::run(const Inputs& in) {
     const int cin = b2 ? 288 : 256;
     const Act* dst = &Xb[i + 1];
     const int dst_halo = (i == 8) ? 0 : 1;
+    uint32_t *f1 = nullptr, *fs = nullptr, *a1 = nullptr, *f2 = nullptr, *a2 = nullptr;
+    if (fm) { f1 = alloc_flags(); fs = b2 ? alloc_flags() : nullptr; a1 = alloc_flags(); f2 = alloc_flags(); a2 = alloc_flags(); }
+    const FlagWait in_ready = fm ? FW(a_prev, apply_n) : none;
     Raw rs;
     Raw r1 = raw(B, 64, 64, 256, true);
-    AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 1), src, 0, W(b + ".conv_block.1"), r1, 0));
+    AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 1), src, 0, W(b + ".conv_block.1"), r1, 0, in_ready, f1));
     if (b2) {
-      // the shortcut conv only depends on the block input: it runs on a side stream, under it the
-      // HBM-bound InstanceNorm apply of conv_block.1
       rs = raw(B, 64, 64, 256, true);
-      AP_TRY(order_after(s1, main_st));
-      on(s1);
-      AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0));
+      if (!fm) {
+        // the shortcut conv only depends on the block input: side stream, under it the apply of conv_block.1
+        AP_TRY(order_after(s1, main_st));
+        on(s1);
+      }
+      AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0, in_ready, fs));
       on(main_st);
     }
-    AP_TRY(apply(r1, 0, 256, 1, &T, 0, 1));
+    on(sA);
+    AP_TRY(apply(r1, 0, 256, 1, &T, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, fm ? FW(f1, conv_n) : none, none, a1));
+    on(main_st);
     Raw r2 = raw(B, 64, 64, 256, true);
-    AP_TRY(conv(geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, 0, W(b + ".conv_block.5"), r2, 0));
-    if (b2) AP_TRY(order_after(main_st, s1));
-    if (b2) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1]));
+    AP_TRY(conv(geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, 0, W(b + ".conv_block.5"), r2, 0, fm ? FW(a1, apply_n) : none, f2));
+    if (b2 && !fm) AP_TRY(order_after(main_st, s1));
+    on(sA);
+    const FlagWait w2 = fm ? FW(f2, conv_n) : none;
+    if (b2) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1], nullptr, w2, fm ? FW(fs, conv_n) : none, a2));
     else if (res_from_act) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, nullptr, nullptr, &src));
-    else AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, xres[i], xres[i + 1]));
+    else AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, xres[i], xres[i + 1], nullptr, w2, none, a2));
+    on(main_st);
+    a_prev = a2;
     const std::string tn = "block" + std::to_string(i);
     if (res_from_act) tap_act(tn.c_str(), *dst, 0, 256);
     else tap_f32(tn.c_str(), xres[i + 1], B, 64, 64, 256);
   }
+  if (fm) AP_TRY(order_after(main_st, sA));
 
   // ---- decoder (networks.py:1268-1279): two ConvT as 4 output phases each, then the 7x7 output conv ----
   Raw ru0 = raw(B, 128, 128, 128, true);
@@ -660,6 +698,13 @@ int ap_netg_create(ap_netg** handle, int output_nc, int precision, int device) {
   h->onc = output_nc; h->prec = precision; h->device = device;
   const char* ov = getenv("AP_NETG_OVERLAP");
   h->overlap = !(ov && ov[0] == '0');
+  // Flag sync (EXPERIMENTAL, opt-in with AP_NETG_FLAGSYNC=1): +3..11 % when it runs, but persistent spinning consumer
+  // CTAs placed two to an SM can keep a CTA pair of the conv they wait for from ever being placed (static item
+  // assignment) -- an intermittent dead-lock that the watchdogs turn into a launch failure.  It needs a dynamic tile
+  // scheduler in the conv before it can be the default.
+  const char* fs = getenv("AP_NETG_FLAGSYNC");
+  h->flagsync = (fs && fs[0] == '1') && precision == AP_PREC_FP32X3 && umma_pairs_available() &&
+                umma_pair_regs_per_cta() + apply_flags_regs_per_cta() <= 65536;
   const char* cp = getenv("AP_NETG_CONVT_PACKED");
   h->convt_packed = !(cp && cp[0] == '0');
   const char* ou = getenv("AP_NETG_OUT_UMMA");
