@@ -215,7 +215,8 @@ struct UmmaConv;  // opaque launch record (tensor maps + params), see conv_umma.
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff,
                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int nprod,
                      float* out_raw, int out_C, int out_coff, double* stats, int stat_C, int stat_coff,
-                     const PhasePack* pk = nullptr, FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done_flags = nullptr);
+                     const PhasePack* pk = nullptr, FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done_flags = nullptr,
+                     const ApplyP* fuse = nullptr);
 uint32_t umma_conv_done_per_image(const UmmaConv* c);
 bool umma_pairs_available();  // CTA-pair kernels enabled and launchable on this device
 int umma_pair_regs_per_cta(); // registers one CTA of the trunk pair kernel occupies  // what done_flags[img] reaches when image img is complete

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "umma.cuh"
+#include "apply_device.cuh"
 
 namespace ap {
 
@@ -57,12 +58,17 @@ struct alignas(64) UmmaParams {
   int l2_hints;  // bit 0: raw output stores evict_last (AP_NETG_L2_HINTS)
   FlagWait wait;         // pair kernel: per-image readiness of the input activations (flag sync), or {null, 0}
   uint32_t* done_flags;  // pair kernel: += 32-column blocks finished per image, or null
+  // FUSED variant: eight extra warps run the InstanceNorm apply pass of THIS conv's output inside the same CTAs, image
+  // by image as done_flags says the image is complete -- the HBM-bound pass hides under the tensor-bound one, and being
+  // warps of the same resident CTAs they can never be starved of an SM the way a separate spinning kernel can.
+  ApplyP fuse;
   int dbg;  // timing diagnostics only (AP_UMMA_DBG): 1 = no TMA loads after the first fill, 2 = no output stores, 4 = no statistics
 };
 
 struct UmmaConv {
   UmmaParams p;
   int BN, nprod, cg;
+  bool fused;
   dim3 grid;
   size_t smem;
 };
@@ -368,8 +374,8 @@ __device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int B
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) runs tcgen05.mma.cta_group::2
 // with M = 256; each CTA stages its own A tile and half of the weight tile, the leader (cluster rank 0) issues.
 // PACKED (phase-packed transposed convs): statistics accumulated on chip over contiguous item runs, one staging slab.
-template <int BN, int NPROD, int CG, bool PACKED>
-__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
+template <int BN, int NPROD, int CG, bool PACKED, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   using Cfg = UmmaCfg<BN, NPROD, CG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int PLANES = Cfg::PLANES;
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row0 = q * 32;
@@ -622,6 +628,12 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
     __syncwarp();
+  } else if (FUSED) {
+    // ===================== fused InstanceNorm apply (warps 6..13) =====================
+    const int tid = (int)threadIdx.x - 192;
+    if (p.fuse.raw2) apply_flag_items<1, 8>(p.fuse, tid, (int)blockIdx.x, (int)gridDim.x);
+    else if (p.fuse.res_in) apply_flag_items<2, 8>(p.fuse, tid, (int)blockIdx.x, (int)gridDim.x);
+    else apply_flag_items<0, 8>(p.fuse, tid, (int)blockIdx.x, (int)gridDim.x);
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // the peer's shared memory / barriers stay valid until both CTAs are done
@@ -654,11 +666,14 @@ template <int BN, int NPROD>
 static int set_attr() {
   AP_CUDA(cudaFuncSetAttribute(conv_umma1_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)UmmaCfg<BN, NPROD, 1>::SMEM));
-  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)pair_smem<BN, NPROD, false>()));
   if (BN == 256)
-    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, NPROD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, NPROD, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pair_smem<256, NPROD, true>()));
+  if (BN == 256 && NPROD == 3)
+    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, 3, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pair_smem<256, 3, false>()));
   return AP_OK;
 }
 
@@ -733,7 +748,7 @@ static int max_pairs_of() {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2, false>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2, false, false>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = 0;
   }
@@ -751,7 +766,7 @@ static int max_pairs(int BN, int nprod) {
 // out-of-bounds with zeros); reflect-padded ones address the haloed buffer (halo = in.pad >= conv pad).
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
                      const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, double* stats,
-                     int stat_C, int stat_coff, const PhasePack* pk, FlagWait wait, uint32_t* done_flags) {
+                     int stat_C, int stat_coff, const PhasePack* pk, FlagWait wait, uint32_t* done_flags, const ApplyP* fuse) {
   AP_TRY(umma_init());
   AP_REQUIRE(in.fmt == FMT_BF16X2 || in.fmt == FMT_BF16, AP_ERR_INVALID, "umma conv needs bf16 activations");
   AP_REQUIRE(nprod == 1 || (nprod == 3 && in.fmt == FMT_BF16X2 && w_lo), AP_ERR_INVALID, "umma conv: nprod/format");
@@ -844,6 +859,16 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
              "flag sync is implemented in the (unpacked) CTA-pair kernel only");
   p.wait = wait;
   p.done_flags = done_flags;
+  c->fused = false;
+  if (fuse) {
+    AP_REQUIRE(c->cg == 2 && !pk && nprod == 3 && g.Cout == 256 && done_flags != nullptr && fuse->C == 256, AP_ERR_UNSUPPORTED,
+               "fused apply needs the 3-product N = 256 CTA-pair kernel and completion flags");
+    p.fuse = *fuse;
+    p.fuse.wait0 = FlagWait{done_flags, umma_conv_done_per_image(c)};
+    p.fuse.wait1 = FlagWait{nullptr, 0};
+    p.fuse.done_flags = nullptr;
+    c->fused = true;
+  }
   p.n_full = groups - rem;
   p.n_items = p.n_full + rem * split;
   c->grid = dim3((unsigned)((p.n_items < G ? p.n_items : G) * c->cg), 1);
@@ -855,7 +880,7 @@ bool umma_pairs_available() { return umma_init() == AP_OK && g_pair != 0 && max_
 
 int umma_pair_regs_per_cta() {
   cudaFuncAttributes a;
-  if (cudaFuncGetAttributes(&a, (const void*)conv_umma_kernel<256, 3, 2, false>) != cudaSuccess) return 1 << 30;
+  if (cudaFuncGetAttributes(&a, (const void*)conv_umma_kernel<256, 3, 2, false, false>) != cudaSuccess) return 1 << 30;
   return ((a.numRegs + 7) / 8 * 8) * 32 * ((192 / 32 + 3) / 4 * 4);
 }
 
@@ -885,8 +910,11 @@ static int launch_one(const UmmaConv* c, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (packed) AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, NPROD, 2, true>, c->p));
-    else AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2, false>, c->p));
+    if (packed) AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, NPROD, 2, true, false>, c->p));
+    else if (c->fused) {
+      cfg.blockDim = dim3(192 + AF_THREADS, 1, 1);
+      AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, 3, 2, false, true>, c->p));
+    } else AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2, false, false>, c->p));
   }
   launches_add(1);
   return AP_OK;

@@ -168,6 +168,7 @@ struct ap_netg {
   bool profiling = false;
   bool overlap = true;  // run independent branches on side streams (AP_NETG_OVERLAP=0 turns it off)
   bool out_umma = true; // tcgen05 output stage (AP_NETG_OUT_UMMA=0: CUDA-core kernel)
+  bool fuse_apply = false;   // trunk: the apply pass of a conv runs in eight extra warps of the same kernel (AP_NETG_FUSE_APPLY=1: on)
   bool flagsync = false;     // trunk: apply passes run under the convs, per-image device flags (AP_NETG_FLAGSYNC=1: on)
   bool convt_packed = true;  // transposed convs as one phase-packed N=256 conv (AP_NETG_CONVT_PACKED=0: four phase convs)
   std::vector<cudaEvent_t> ev;      // ev[0] = start, ev[i+1] = after launch i
@@ -307,7 +308,7 @@ struct Runner {
 
   // A 3x3 / transposed-conv layer on the tensor-core or the CUDA-core path, by handle precision.
   int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff,
-           FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done = nullptr) {
+           FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done = nullptr, const ApplyP* fuse = nullptr) {
     if (h->prec == AP_PREC_FP32_SIMT) {
       if (ph != PH_EXEC) return AP_OK;
       SimtConvP p{};
@@ -323,7 +324,7 @@ struct Runner {
     if (ph == PH_BUILD) {
       UmmaConv* c = nullptr;
       AP_TRY(umma_conv_create(&c, g, in, in_coff, w.hi, w.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C,
-                              out_coff, out.stats, out.C, out_coff, nullptr, wait, done));
+                              out_coff, out.stats, out.C, out_coff, nullptr, wait, done, fuse));
       pl->convs.push_back(c);
       return AP_OK;
     }
@@ -364,10 +365,8 @@ struct Runner {
     AP_TRY(launch_conv_simt(p, st));
     return mark(g.taps.n == 49 ? CL_STEM : CL_LAND, conv_flops(g));
   }
-  int apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias = nullptr,
-            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr, const Act* res_act = nullptr,
-            FlagWait fl_w0 = FlagWait{nullptr, 0}, FlagWait fl_w1 = FlagWait{nullptr, 0}, uint32_t* fl_done = nullptr) {
-    if (ph != PH_EXEC) return AP_OK;
+  static ApplyP make_apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias,
+                           const Raw* r2, const float* res_in, float* res_out, const Act* res_act) {
     ApplyP p{};
     p.raw = r.p; p.raw_C = r.C; p.raw_coff = rcoff;
     p.stats = r.stats; p.stat_C = r.C; p.stat_coff = rcoff;
@@ -381,12 +380,30 @@ struct Runner {
     if (dst) { p.fmt = dst->fmt; p.d0 = dst->p0; p.d1 = dst->p1; p.dC = dst->C; p.dcoff = dcoff; p.dpad = dst->pad; }
     else p.fmt = -1;
     p.halo_reflect = halo;
+    return p;
+  }
+  int apply(const Raw& r, int rcoff, int C, int relu, const Act* dst, int dcoff, int halo, const float* bias = nullptr,
+            const Raw* r2 = nullptr, const float* res_in = nullptr, float* res_out = nullptr, const Act* res_act = nullptr,
+            FlagWait fl_w0 = FlagWait{nullptr, 0}, FlagWait fl_w1 = FlagWait{nullptr, 0}, uint32_t* fl_done = nullptr) {
+    if (ph != PH_EXEC) return AP_OK;
+    ApplyP p = make_apply(r, rcoff, C, relu, dst, dcoff, halo, bias, r2, res_in, res_out, res_act);
     if (fl_done != nullptr || fl_w0.flags != nullptr) {
       p.wait0 = fl_w0; p.wait1 = fl_w1; p.done_flags = fl_done;
       AP_TRY(launch_apply_flags(p, st));
     } else {
       AP_TRY(launch_apply(p, st));
     }
+    return mark(CL_APPLY, 0.0);
+  }
+  // A trunk conv whose InstanceNorm apply pass runs inside the same kernel (conv_umma.cu, FUSED), or conv + apply launch.
+  int conv_apply(bool fused, const ConvGeom& g, const Act& in, const LayerW& w, const Raw& out, const ApplyP& ap_) {
+    if (fused) {
+      uint32_t* done = alloc_flags();
+      return conv(g, in, 0, w, out, 0, FlagWait{nullptr, 0}, done, &ap_);
+    }
+    AP_TRY(conv(g, in, 0, w, out, 0));
+    if (ph != PH_EXEC) return AP_OK;
+    AP_TRY(launch_apply(ap_, st));
     return mark(CL_APPLY, 0.0);
   }
   int warp(const Raw& r, int rcoff, int C, int level, const Inputs& in, const Act& dst, int dcoff) {
@@ -556,6 +573,37 @@ int Runner::run(const Inputs& in) {
   // apply passes on ONE side stream; they are ordered per image by device-side counters, so an apply pass runs under
   // the conv that feeds it and the next conv starts on images that are already applied.  Otherwise: stream order, the
   // shortcut conv of a ResnetBlock2 on a side stream under conv1's apply.
+  const bool fu = h->fuse_apply && h->prec == AP_PREC_FP32X3 && !flag_mode();
+  if (fu) {
+    // Fused mode: every trunk conv kernel carries the apply pass of its own output in eight extra warps.
+    Raw rM = raw(B, 64, 64, 256, false);
+    AP_TRY(conv_apply(true, geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, W("model_tri_merge"), rM,
+                      make_apply(rM, 0, 256, 0, &Xb[0], 0, 1, h->b_merge, nullptr, nullptr, xres[0], nullptr)));
+    tap_f32("merge", xres[0], B, 64, 64, 256);
+    AP_TRY(order_after(main_st, s3));
+    for (int i = 0; i < 9; ++i) {
+      const std::string b = "model2." + std::to_string(i);
+      const bool b2 = (i % 3) == 0;
+      const Act& src = Xb[i];
+      const int cin = b2 ? 288 : 256;
+      const Act* dst = &Xb[i + 1];
+      const int dst_halo = (i == 8) ? 0 : 1;
+      Raw r1 = raw(B, 64, 64, 256, true);
+      AP_TRY(conv_apply(true, geom_conv(B, 64, cin, 256, 3, 1, 1, 1), src, W(b + ".conv_block.1"), r1,
+                        make_apply(r1, 0, 256, 1, &T, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr)));
+      Raw rs;
+      if (b2) {
+        rs = raw(B, 64, 64, 256, true);
+        AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0));
+      }
+      Raw r2 = raw(B, 64, 64, 256, true);
+      AP_TRY(conv_apply(true, geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, W(b + ".conv_block.5"), r2,
+                        b2 ? make_apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1], nullptr)
+                           : make_apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, nullptr, xres[i], xres[i + 1], nullptr)));
+      const std::string tn = "block" + std::to_string(i);
+      tap_f32(tn.c_str(), xres[i + 1], B, 64, 64, 256);
+    }
+  } else {
   const bool fm = flag_mode();
   const uint32_t conv_n = (uint32_t)(64 * 64 / 128) * 4u * (256u / 32u);  // == umma_conv_done_per_image of a 64x64, N=256 conv
   const uint32_t apply_n = apply_flags_done_per_image(64, 64);
@@ -618,6 +666,7 @@ int Runner::run(const Inputs& in) {
     else tap_f32(tn.c_str(), xres[i + 1], B, 64, 64, 256);
   }
   if (fm) AP_TRY(order_after(main_st, sA));
+  }  // !fu
 
   // ---- decoder (networks.py:1268-1279): two ConvT as 4 output phases each, then the 7x7 output conv ----
   Raw ru0 = raw(B, 128, 128, 128, true);
@@ -702,6 +751,10 @@ int ap_netg_create(ap_netg** handle, int output_nc, int precision, int device) {
   // CTAs placed two to an SM can keep a CTA pair of the conv they wait for from ever being placed (static item
   // assignment) -- an intermittent dead-lock that the watchdogs turn into a launch failure.  It needs a dynamic tile
   // scheduler in the conv before it can be the default.
+  const char* fa = getenv("AP_NETG_FUSE_APPLY");
+  // Opt-in: parity-green and dead-lock free, but measured neutral (2322-2327 vs 2325-2336 frames/s): the conv kernel gets
+  // longer by what the apply pass took -- the step is power-capped, overlapping work does not remove its energy.
+  h->fuse_apply = (fa && fa[0] == '1') && precision == AP_PREC_FP32X3 && umma_pairs_available();
   const char* fs = getenv("AP_NETG_FLAGSYNC");
   h->flagsync = (fs && fs[0] == '1') && precision == AP_PREC_FP32X3 && umma_pairs_available() &&
                 umma_pair_regs_per_cta() + apply_flags_regs_per_cta() <= 65536;
