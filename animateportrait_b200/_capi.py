@@ -1,4 +1,4 @@
-"""ctypes binding of libapnetg.so (include/ap_netg.h). No fallback: a missing or unloadable library raises."""
+"""ctypes binding of libapnetg.so (include/ap_netg.h, include/ap_cond.h). No fallback: a missing or unloadable library raises."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,7 +14,7 @@ AP_PREC_BF16 = 1
 AP_PREC_FP32_SIMT = 2
 PRECISIONS = {"fp32": AP_PREC_FP32X3, "fp32x3": AP_PREC_FP32X3, "bf16": AP_PREC_BF16, "fp32_simt": AP_PREC_FP32_SIMT}
 
-# every symbol include/ap_netg.h declares: (restype, argtypes)
+# every symbol include/*.h declares: (restype, argtypes)
 _FP = C.POINTER(C.c_float)
 SYMBOLS = {
     "ap_netg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
@@ -31,6 +31,13 @@ SYMBOLS = {
                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "ap_netg_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.c_void_p]),
     "ap_conv2d_debug": (C.c_int, [C.c_int] * 12 + [C.c_void_p] * 5),
+    # include/ap_cond.h
+    "ap_cond_draw_landmarks": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 3),
+    "ap_cond_motion256": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p, C.c_void_p]),
+    "ap_cond_motion256_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    "ap_cond_kp_to_map": (C.c_int, [C.c_int] * 4 + [C.c_float] + [C.c_void_p] * 3),
+    "ap_cond_matte_photo": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 5),
     "ap_last_error": (C.c_char_p, []),
     "ap_version": (C.c_char_p, []),
 }

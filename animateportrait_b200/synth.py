@@ -164,3 +164,72 @@ def flops_per_frame(output_nc: int = 1) -> float:
         # model3.0/.3 are transposed convs: MACs counted on the INPUT resolution (Appendix A.4)
         total += 2.0 * macs_per_px * r * r * n
     return total
+
+
+# --------------------------------------------------------------------------------------
+# synthetic clip: one photo + a landmark trajectory standing in for Module1's output
+# --------------------------------------------------------------------------------------
+def face_template():
+    """A plausible 68-point layout in the 256x256 window (jaw arc, brows, nose, eyes, two mouth rings), float32 [68,2]."""
+    import numpy as np
+    p = []
+    for i in range(17):                      # jaw
+        a = np.pi * (0.08 + 0.84 * i / 16)
+        p.append([128 - 78 * np.cos(a), 118 + 92 * np.sin(a)])
+    for i in range(5):
+        p.append([62 + 11 * i, 92 - 6 * np.sin(np.pi * i / 4)])    # right brow
+    for i in range(5):
+        p.append([150 + 11 * i, 92 - 6 * np.sin(np.pi * i / 4)])   # left brow
+    for i in range(4):
+        p.append([128, 104 + 11 * i])                              # nose bridge
+    for i in range(5):
+        p.append([110 + 9 * i, 150 + 3 * np.sin(np.pi * i / 4)])   # nostrils
+    for cx in (84, 172):                                           # eyes
+        for i in range(6):
+            a = 2 * np.pi * i / 6
+            p.append([cx - 13 * np.cos(a), 112 - 6 * np.sin(a)])
+    for i in range(12):                                            # outer lips
+        a = 2 * np.pi * i / 12
+        p.append([128 - 28 * np.cos(a), 182 - 11 * np.sin(a)])
+    for i in range(8):                                             # inner lips
+        a = 2 * np.pi * i / 8
+        p.append([128 - 17 * np.cos(a), 182 - 5 * np.sin(a)])
+    return np.asarray(p, dtype=np.float32)
+
+
+def landmark_sequence(T: int, seed: int = 0, amp: float = 4.0):
+    """(source landmarks [68,2], target sequence [T,68,2]) float32 tensors: template + jitter, then a smooth head sway
+    plus a mouth opening cycle (Module1 cannot run here).  Same recipe as oracle/cond_oracle.py."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    src = face_template() + rng.normal(0, 0.7, (68, 2)).astype(np.float32)
+    t = np.arange(T, dtype=np.float32)[:, None, None]
+    sway = np.concatenate([amp * np.sin(2 * np.pi * t / 90.0), 0.5 * amp * np.sin(2 * np.pi * t / 57.0 + 1.0)], 2)
+    seq = src[None] + sway
+    mouth = np.zeros((1, 68, 2), dtype=np.float32)
+    mouth[0, 48:68, 1] = (src[48:68, 1] - 182.0) * 0.6
+    seq = seq + mouth * (0.5 + 0.5 * np.sin(2 * np.pi * t / 11.0))
+    seq = seq + rng.normal(0, 0.15, seq.shape)
+    return torch.from_numpy(src.astype(np.float32)), torch.from_numpy(seq.astype(np.float32))
+
+
+def make_clip(T: int, output_nc: int = 1, seed: int = 2000):
+    """Synthetic clip: photo [1,3,256,256], matte [1,1,256,256], static drawing [1,onc,256,256], source landmarks [68,2],
+    target landmarks [T,68,2], and per-frame intrinsic flow [T,2,256,256] / visibility mask [T,1,256,256] standing in
+    for the flow network's output (netF, SURVEY.md §8 row f3, is not built)."""
+    g = torch.Generator().manual_seed(seed)
+    photo = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    lin = torch.linspace(-1, 1, 256)
+    yy, xx = torch.meshgrid(lin, lin, indexing="ij")
+    ell = (((xx / 0.7) ** 2 + ((yy - 0.05) / 0.85) ** 2) <= 1.0).float()[None, None]
+    matte = F.avg_pool2d(ell, 9, stride=1, padding=4).clamp(0, 1)
+    static = torch.rand(1, output_nc, 256, 256, generator=g) * 2 - 1
+    src, seq = landmark_sequence(T, seed=seed)
+    coarse = torch.randn(8, 2, 8, 8, generator=g) * 4.0      # 8 key flows, cycled and blended along the clip
+    key = F.interpolate(coarse, size=(256, 256), mode="bilinear", align_corners=True) * ell
+    w = (torch.arange(T, dtype=torch.float32) / 12.0)
+    i0 = w.floor().long() % 8
+    a = (w - w.floor())[:, None, None, None]
+    flow = (1 - a) * key[i0] + a * key[(i0 + 1) % 8]
+    ifmask = matte.expand(T, 1, 256, 256).contiguous()
+    return photo, matte, static, src, seq, flow.contiguous(), ifmask

@@ -2,12 +2,16 @@
 """Benchmark of the Module2 netG hot path: generator frames/s at 256x256 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16|fp32_simt]
-                    [--batch B] [--output-nc 1|3]
+                    [--batch B] [--output-nc 1|3] [--workload batch|clip] [--frames T]
 
 A step = one generator forward over one batch of B synthetic frames per GPU (BASELINE.json configs[1]:
 batch=16 frames, 1xB200, fp32-accurate, line drawing).  N>1 is launched by torchrun, one rank per GPU; frames
 shard data-parallel with no collective in the data path (weak scaling: B frames per GPU).
 Prints ONE JSON line on rank 0.
+
+`--workload clip` is BASELINE.json configs[2] (one photo, the T = 733 target landmark sets of a 12 s clip, bf16 convs):
+a step = one pass over the whole clip through animateportrait_b200.clip.ClipRenderer -- landmark maps and the Delaunay
+motion field made on the GPU from the 68x2 coordinates, generator, blend with the static drawing, uint8 frames.
 
 `--impl reference` times the reference's CPU implementation of the same path on the host cores: the
 oracle port of it (oracle/netg_oracle.py, bit-identical to the PyTorch reference, see tests/golden) --
@@ -130,25 +134,271 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+CLIP_METRIC_NOTE = ("configs[2]: one photo + {T} target landmark sets (12 s clip), landmark maps + Delaunay motion field on the "
+                    "GPU, netG output_nc={onc} precision={prec} in batches of {B}, blend with the static drawing, uint8 frames; "
+                    "intrinsic flow / visibility mask are device-resident stand-ins for netF's output (not built)")
+
+
+def _cpu_clip_frames(sd, clip, frames):
+    """The reference's per-frame loop on the CPU for the given frame indices (oracle port, batch size 1 as
+    Module2/test.py:42): cal_motion256 through scipy's griddata -- the reference's own call -- when scipy is installed."""
+    import numpy as np
+    import torch
+    from oracle import cond_oracle as OC
+    from oracle import netg_oracle as O
+    photo, matte, static, src, seq, flow, ifmask = clip
+    try:
+        from scipy.interpolate import griddata
+    except Exception:  # pragma: no cover
+        griddata = None
+    real_A, mask = OC.matte_photo(photo.numpy(), matte.numpy())
+    real_A, mask = torch.from_numpy(real_A), torch.from_numpy(mask)
+    land1 = torch.from_numpy(OC.draw_landmarks(src.numpy()[None]))
+    ys, xs = np.mgrid[0:256, 0:256]
+    for t in frames:
+        land2 = torch.from_numpy(OC.draw_landmarks(seq[t:t + 1].numpy()))
+        if griddata is not None:
+            sites, vals = OC.motion_sites(src.numpy(), seq[t].numpy())
+            m = griddata(sites, vals, (xs.astype(np.float64), ys.astype(np.float64)), method="linear").astype(np.float32)
+            motion = torch.from_numpy(m / np.float32(127.5) - np.float32(1))[None]
+        else:
+            motion = torch.from_numpy(OC.cal_motion(src.numpy(), seq[t].numpy()))[None]
+        fake = O.netg_forward(sd, real_A, land1, land2, motion, flow[t:t + 1], ifmask[t:t + 1])
+        O.tensor2im_batch(O.blend_foreground(fake, mask, motion, static))
+    return griddata is not None
+
+
+def _time_cpu_clip(args, n_frames, steps, warmup):
+    import torch
+    from animateportrait_b200 import synth
+    from oracle import netg_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.make_state_dict(args.output_nc, seed=0)
+    clip = synth.make_clip(max(n_frames, 8), args.output_nc, seed=2000)
+    frames = list(range(n_frames))
+    for _ in range(warmup):
+        _cpu_clip_frames(sd, clip, frames[:1])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        used_scipy = _cpu_clip_frames(sd, clip, frames)
+    dt = time.perf_counter() - t0
+    return n_frames * steps / dt, dt / steps, torch.get_num_threads(), used_scipy
+
+
+def run_reference_clip(args, rank):
+    """Reference arm of the clip workload: the per-frame CPU loop on a bounded sample of the clip's frames."""
+    if rank != 0:
+        return
+    import torch
+    n = 8
+    fps, step_s, cores, used_scipy = _time_cpu_clip(args, n, args.steps, max(args.warmup, 1))
+    sample = (f"{args.steps} steps x {n} frames of the clip, one frame at a time (reference batch size 1), torch "
+              f"{torch.__version__} CPU ops on all host threads, motion field by "
+              f"{'scipy griddata (the reference call)' if used_scipy else 'the numpy restatement'}")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CLIP_METRIC_NOTE.format(T=args.frames, onc=args.output_nc, prec="fp32 (CPU)", B=1)
+                       + f"; step = {n}-frame sample of the clip"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_clip(args, rank, local_rank, world):
+    """BASELINE.json configs[2] on N GPUs: frames of ONE clip shard over the ranks (strong scaling); only the target
+    landmarks are scattered (68x2 floats per frame), uint8 frames are gathered on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import animateportrait_b200 as ap
+    from animateportrait_b200 import synth
+    from animateportrait_b200.clip import ClipRenderer
+    from animateportrait_b200.frames import _gather, _scatter, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the generator")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    T, B, onc = args.frames, args.batch, args.output_nc
+    net = ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [local_rank], div=3, disp=3,
+                      precision=args.precision).module
+    net.load_state_dict(synth.make_state_dict(onc, seed=0))
+    photo, matte, static, src, seq, flow, ifmask = synth.make_clip(T, onc, seed=2000)
+    lo, hi = shard_range(T, world, rank)
+    # netF stand-in: every rank holds the flow / visibility mask of its own frames, as a per-rank flow network would
+    flow_d, ifm_d = flow[lo:hi].to(dev), ifmask[lo:hi].to(dev)
+    seq_host = seq.pin_memory()
+    seq_dev = seq.to(dev) if rank == 0 else None
+    r = ClipRenderer(net, batch=B)
+    r.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
+    mine = torch.empty((hi - lo, 256, 256, 3), dtype=torch.uint8, device=dev)
+    frames_host = torch.empty((T, 256, 256, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass(lm_rank0):
+        lm = _scatter(lm_rank0, (68, 2), T, dev, None) if world > 1 else lm_rank0
+        if hi > lo:
+            r.render(lm, flow_d, ifm_d, out=mine)
+        return _gather(mine, T, None) if world > 1 else mine
+
+    # ---------------- device-resident: landmarks already in HBM, frames stay in HBM ----------------
+    for _ in range(args.warmup):
+        one_pass(seq_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_pass(seq_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    value = T * args.steps / (ms_max * 1e-3)
+
+    # ---------------- end to end: host landmarks in, host uint8 frames out ----------------
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def one_e2e():
+        lm0 = seq_host.to(dev, non_blocking=True) if rank == 0 else None
+        fr = one_pass(lm0)
+        if rank == 0:
+            frames_host.copy_(fr, non_blocking=True)
+        torch.cuda.synchronize()
+
+    one_e2e()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        one_e2e()
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e = {"value": T * e2e_steps / (t2.item() * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * 68 * 2 * 4,
+           "d2h_bytes_per_step": T * 256 * 256 * 3,
+           "path": "pinned host target landmarks -> H2D -> (NCCL scatter) -> ClipRenderer.render per rank -> (NCCL gather) -> "
+                   "D2H uint8 frames -> sync, every step"}
+
+    # ---------------- per-kernel-class device time of the generator + the conditioning kernels ----------------
+    peaks = measured_peaks()
+    nb = min(B, hi - lo)
+    lm_b = seq[lo:lo + nb].to(dev)
+    from animateportrait_b200 import conditioning as cond
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for _ in range(2):
+        ev[0].record()
+        cond.draw2(256, 256, lm_b, 3)
+        ev[1].record()
+        motion_b = cond.cal_motion256(src.to(dev), lm_b)
+        ev[2].record()
+    torch.cuda.synchronize()
+    cond_ms = {"draw2": ev[0].elapsed_time(ev[1]), "cal_motion256": ev[1].elapsed_time(ev[2])}
+    photo_b, land1_b = r._expanded(nb)[:2]
+    land2_b = cond.draw2(256, 256, lm_b, 3)
+    net.set_profiling(True)
+    prof = None
+    with torch.no_grad():
+        for _ in range(3):
+            net(photo_b, land1_b, land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
+            p = net.get_profile()
+            if prof is None:
+                prof = p
+            else:
+                for k in p:
+                    for f in ("ms", "launches", "flops"):
+                        prof[k][f] += p[k][f]
+    net.set_profiling(False)
+    trunk = prof["trunk_conv3x3"]
+    trunk_tflops = trunk["flops"] / (trunk["ms"] * 1e-3) / 1e12 if trunk["ms"] > 0 else 0.0
+    nprod = {"fp32": 3, "bf16": 1, "fp32_simt": 0}[args.precision]
+    step_prof = sum(v["ms"] for v in prof.values()) / 3.0
+    roofline = {"bound": "tensor", "kernel": f"conv_umma_kernel (3x3 s1 trunk convs @64x64, 22 launches per {nb}-frame batch)",
+                "achieved": trunk_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": trunk_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                "mma_tflops": trunk_tflops * max(nprod, 1),
+                "frac_of_mma_ceiling": trunk_tflops * max(nprod, 1) / peaks["bf16_tflops_sustained"],
+                "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
+                "algorithmic_flops_per_launch": trunk["flops"] / max(trunk["launches"], 1),
+                "avg_launch_ms": trunk["ms"] / max(trunk["launches"], 1), "mma_products_per_flop": nprod,
+                "share_of_step": trunk["ms"] / 3.0 / step_prof if step_prof else None,
+                "classes_ms_per_batch": {k: round(v["ms"] / 3.0, 4) for k, v in prof.items()},
+                "conditioning_ms_per_batch": {k: round(v, 4) for k, v in cond_ms.items()}}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            fps, step_s, cores, used_scipy = _time_cpu_clip(args, 8, 2, 1)
+            cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "2 x 8 frames of the clip, frame by frame (reference batch size 1), oracle port of the "
+                                      "reference's loop on all host threads, motion field by "
+                                      + ("scipy griddata (the reference call)" if used_scipy else "the numpy restatement")}
+        n_batches = sum(-(-(shard_range(T, world, q)[1] - shard_range(T, world, q)[0]) // B) for q in range(world))
+        launches_per_step = n_batches * (net.last_launch_count() + 4)   # + draw2, delaunay, raster, compose per batch
+        flops_frame = synth.flops_per_frame(onc)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"fp32": "bf16x3 (hi/lo split, fp32 accumulate; fp32-accurate)", "bf16": "bf16",
+                          "fp32_simt": "f32"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": CLIP_METRIC_NOTE.format(T=T, onc=onc, prec=args.precision, B=B),
+                           "l2": f"every batch touches a {net.workspace_bytes(min(B, T)) / 1e9:.1f} GB working set (> 126 MB L2); "
+                                 "per-frame inputs differ for every frame of the clip",
+                           "parallelism": f"dp{world} (frames of one clip sharded; landmark scatter + frame gather only)"},
+                "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "model_tflops": value * flops_frame / 1e12,
+                "tensor_frac_of_sustained_bf16": value / world * flops_frame / 1e12 / peaks["bf16_tflops_sustained"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
-    ap_.add_argument("--steps", type=int, default=100)
+    ap_.add_argument("--steps", type=int, default=None)
     ap_.add_argument("--warmup", type=int, default=5)
+    ap_.add_argument("--workload", default="batch", choices=["batch", "clip"])
+    ap_.add_argument("--frames", type=int, default=733, help="clip workload: frames per clip (12 s of audio = 733)")
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap_.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
-    ap_.add_argument("--batch", type=int, default=16)
+    ap_.add_argument("--precision", default=None, choices=["fp32", "bf16", "fp32_simt"])
+    ap_.add_argument("--batch", type=int, default=None)
     ap_.add_argument("--output-nc", type=int, default=1, dest="output_nc")
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     args = ap_.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    clip = args.workload == "clip"
+    if args.steps is None:
+        args.steps = (5 if clip else 100) if args.impl == "ours" else (2 if clip else 5)
+    if args.precision is None:
+        args.precision = "bf16" if clip else "fp32"      # configs[2] is quoted on bf16 convs, configs[1] on fp32
+    if args.batch is None:
+        args.batch = 32 if clip else 16
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        (run_reference_clip if clip else run_reference)(args, rank)
+        return
+    if clip:
+        run_clip(args, rank, local_rank, world)
         return
 
     import torch

@@ -1,4 +1,4 @@
-"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/ap_netg.h declares."""
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/*.h declares."""
 import ctypes
 import os
 import re
@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    txt = open(os.path.join(ROOT, "include", "ap_netg.h")).read()
+    txt = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include")))
+                  if h.endswith(".h"))
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(ap_[a-z0-9_]+)\s*\(", txt)))
 
@@ -18,7 +19,9 @@ def _declared():
 def test_header_declares_the_documented_entry_points():
     d = _declared()
     for name in ["ap_netg_create", "ap_netg_destroy", "ap_netg_load_weights", "ap_netg_workspace_bytes",
-                 "ap_netg_forward", "ap_netg_forward_host", "ap_netg_debug_read", "ap_last_error", "ap_version"]:
+                 "ap_netg_forward", "ap_netg_forward_host", "ap_netg_debug_read", "ap_last_error", "ap_version",
+                 "ap_cond_draw_landmarks", "ap_cond_motion256", "ap_cond_motion256_workspace_bytes", "ap_cond_kp_to_map",
+                 "ap_cond_matte_photo"]:
         assert name in d
 
 
@@ -54,3 +57,14 @@ def test_invalid_arguments_return_error_codes_without_a_gpu(built_lib):
     assert b"output_nc" in lib.ap_last_error()
     assert lib.ap_netg_create(ctypes.byref(h), 1, 9, 0) == -1  # AP_ERR_INVALID
     assert lib.ap_netg_forward(None, 1, None, None, None, None, None, None, None, None) == -1
+    # conditioning producers (include/ap_cond.h): argument checks come before any CUDA call
+    assert lib.ap_cond_draw_landmarks(0, 1, 68, 255, 3, None, None, None) == -1
+    assert lib.ap_cond_draw_landmarks(0, 1, 68, 256, 16, ctypes.c_void_p(16), ctypes.c_void_p(16), None) == -1
+    assert b"radius" in lib.ap_last_error()
+    assert lib.ap_cond_motion256(0, 1, ctypes.c_void_p(16), 0, ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 8,
+                                 None, None) == -1
+    assert b"workspace" in lib.ap_last_error()
+    n = ctypes.c_size_t()
+    assert lib.ap_cond_motion256_workspace_bytes(3, ctypes.byref(n)) == 0 and n.value >= 3 * 512 * 16
+    assert lib.ap_cond_kp_to_map(0, 1, 68, 222, 4.0, ctypes.c_void_p(16), ctypes.c_void_p(16), None) == -1
+    assert lib.ap_cond_matte_photo(0, 1, 3, 64, None, ctypes.c_void_p(16), None, None, None) == -1

@@ -1,0 +1,121 @@
+"""Clip-level rendering (animateportrait_b200/clip.py): frame-invariant hoisting + GPU conditioning + netG + output stage.
+
+CPU: the landmark-sharding plumbing over gloo (world_size 2 and 3) with a stand-in renderer, and the synthetic clip
+recipe against the oracle's copy.  GPU (-m gpu): ClipRenderer against the oracle's frame-by-frame restatement of the
+reference's loop (dataset item -> GeomCGTIFWTestModel.forward -> tensor2im)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from animateportrait_b200 import synth
+from animateportrait_b200.clip import ClipRenderer, render_clip_sharded
+from oracle import cond_oracle as OC
+
+
+def test_synthetic_clip_recipe_matches_the_oracles():
+    a, b = synth.landmark_sequence(40, seed=5)
+    c, d = OC.landmark_sequence(40, seed=5)
+    assert np.array_equal(a.numpy(), c) and np.array_equal(b.numpy(), d)
+    photo, matte, static, src, seq, flow, ifmask = synth.make_clip(7, output_nc=3, seed=9)
+    assert photo.shape == (1, 3, 256, 256) and static.shape == (1, 3, 256, 256) and seq.shape == (7, 68, 2)
+    assert flow.shape == (7, 2, 256, 256) and ifmask.shape == (7, 1, 256, 256)
+    assert 0 < float((matte > 0.5).float().mean()) < 1 and float(seq.min()) > 3 and float(seq.max()) < 252
+
+
+def test_renderer_refuses_cpu_tensors_and_missing_photo():
+    r = ClipRenderer(torch.nn.Identity())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        r.set_photo(torch.zeros(1, 3, 256, 256), torch.zeros(68, 2))
+    with pytest.raises(RuntimeError, match="set_photo"):
+        r.render(torch.zeros(2, 68, 2))
+
+
+class _StandInRenderer:
+    """Per-frame function of the landmarks (and flow/mask when given), so a mis-routed frame changes the result."""
+
+    def render(self, lm, flow=None, ifm=None):
+        v = lm.sum((1, 2))
+        if flow is not None:
+            v = v + flow.mean((1, 2, 3)) + 2 * ifm.mean((1, 2, 3))
+        img = (v.abs() * 7).to(torch.int64) % 251
+        return img.to(torch.uint8)[:, None, None, None].expand(-1, 256, 256, 3).contiguous()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _clip(T, with_flow):
+    g = torch.Generator().manual_seed(T)
+    lm = torch.rand(T, 68, 2, generator=g) * 255
+    if not with_flow:
+        return lm, None, None
+    return lm, torch.randn(T, 2, 256, 256, generator=g), torch.rand(T, 1, 256, 256, generator=g)
+
+
+def _worker(rank, world, port, T, with_flow, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lm, flow, ifm = _clip(T, with_flow) if rank == 0 else (None, None, None)
+        frames = render_clip_sharded(_StandInRenderer(), lm, T, torch.device("cpu"), flow, ifm)
+        if rank == 0:
+            torch.save(frames, out_path)
+        else:
+            assert frames is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,T,with_flow", [(2, 5, False), (2, 3, True), (3, 2, False)])
+def test_sharded_clip_equals_single_process(world, T, with_flow, tmp_path):
+    out = str(tmp_path / "frames.pt")
+    mp.spawn(_worker, args=(world, _free_port(), T, with_flow, out), nprocs=world, join=True)
+    got = torch.load(out)
+    want = _StandInRenderer().render(*_clip(T, with_flow))
+    assert got.dtype == torch.uint8 and got.shape == (T, 256, 256, 3) and torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("onc", [1, 3])
+def test_clip_renderer_matches_frame_by_frame_oracle(onc):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import animateportrait_b200 as ap
+    from oracle import netg_oracle as O
+    dev = torch.device("cuda", 0)
+    T = 3
+    sd = O.make_state_dict(onc, seed=3, bias_std=0.3)
+    photo, matte, static, src, seq, flow, ifmask = synth.make_clip(T, output_nc=onc, seed=31 + onc)
+    want_f, want_u8 = OC.render_clip_frames(sd, photo, matte, static, src.numpy(), seq.numpy(), flow, ifmask)
+    net = ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3)
+    net.module.load_state_dict(sd)
+    r = ClipRenderer(net, batch=2)                     # ragged: batches of 2 + 1
+    r.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
+    got_f = r.render(seq, flow.to(dev), ifmask.to(dev), return_tensor=True).cpu()    # host landmarks are accepted
+    got_u8 = r.render(seq.to(dev), flow.to(dev), ifmask.to(dev)).cpu().numpy()
+    assert (got_f - want_f).abs().max().item() <= 1e-3          # north_star's fp32 gate, through the whole frame path
+    d = np.abs(got_u8.astype(np.int16) - want_u8.astype(np.int16))
+    assert got_u8.shape == (T, 256, 256, 3) and d.max() <= 1 and (d > 0).mean() <= 0.1
+    # without matte / static drawing: plain generator frames, zero intrinsic flow and full visibility by default
+    r.set_photo(photo.to(dev), src.to(dev))
+    plain = r.render(seq[:1].to(dev), return_tensor=True).cpu()
+    land1 = torch.from_numpy(OC.draw_landmarks(src.numpy()[None]))
+    land2 = torch.from_numpy(OC.draw_landmarks(seq[:1].numpy()))
+    motion = torch.from_numpy(OC.cal_motion(src.numpy(), seq[0].numpy()))[None]
+    ref = O.netg_forward(sd, photo, land1, land2, motion, torch.zeros(1, 2, 256, 256), torch.ones(1, 1, 256, 256))
+    assert (plain - ref).abs().max().item() <= 1e-3
