@@ -140,6 +140,7 @@ struct WarpP {
   const float* flow;    // [B,2,256,256]
   const float* ifmask;  // [B,1,256,256]
   int B, S, C, level;   // feature size S, feature channels C, pyramid level 0/1/2
+  int src_shared;       // 1: `raw`/`stats` hold ONE image that every frame of the batch warps (clip mode)
   int fmt; void* d0; void* d1; int dC, dcoff, dpad;  // output: 2C channels at dcoff
 };
 

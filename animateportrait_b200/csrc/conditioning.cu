@@ -46,51 +46,69 @@ __device__ __forceinline__ void load_sites(const float* lm, double* sx, double* 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Delaunay by exhaustion: block (i, frame) walks all (j, k), i < j < k, and keeps the triple when no other site lies
-// strictly inside its circumcircle.  C(72,3) = 59,640 triples x <= 69 in-circle determinants, with an early exit that
-// ends most triples after a handful of sites.  In general position the survivors are THE Delaunay triangulation (139
-// triangles); co-circular sites keep every triangulation of their cell, the rasteriser then picks by smallest key.
+// Delaunay by exhaustion: one thread per site triple i < j < k (C(72,3) = 59,640 per frame, unranked from the flat thread
+// index so that every CTA carries the same work); the triple is kept when no other site lies strictly inside its
+// circumcircle.  The in-circle scan starts at the site after i -- landmark indices are spatially coherent, so a
+// neighbour of a vertex is the likeliest site inside a large circle and most triples are rejected after one or two
+// determinants.  In general position the survivors are THE Delaunay triangulation (2n-2-h triangles); co-circular sites
+// keep every triangulation of their cell, the rasteriser then picks by smallest key.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int NTRIPLES = NS * (NS - 1) * (NS - 2) / 6;
+
+__device__ __forceinline__ int triples_before(int i) {  // triples whose first index is < i
+  const int r = NS - i;
+  return NTRIPLES - r * (r - 1) * (r - 2) / 6;
+}
+
 __global__ void __launch_bounds__(128) delaunay_kernel(const float* __restrict__ lm_dst, int* __restrict__ counts,
                                                        TriRec* __restrict__ tris) {
   __shared__ double sx[NS], sy[NS];
-  const int f = blockIdx.y, i = blockIdx.x;
+  __shared__ int before[NS];
+  const int f = blockIdx.y;
   load_sites(lm_dst + (size_t)f * NLM * 2, sx, sy);
+  if (threadIdx.x < NS) before[threadIdx.x] = triples_before(threadIdx.x);
   __syncthreads();
-  const double ax = sx[i], ay = sy[i];
-  const int m = NS - 1 - i;  // sites after i
-  for (int p = threadIdx.x; p < m * m; p += 128) {
-    const int jj = p / m, kk = p - jj * m;
-    if (jj >= kk) continue;
-    const int j = i + 1 + jj, k = i + 1 + kk;
-    const double bx = sx[j], by = sy[j], cx = sx[k], cy = sy[k];
-    const double e1x = dsub(bx, ax), e1y = dsub(by, ay), e2x = dsub(cx, ax), e2y = dsub(cy, ay);
-    const double orient = dsub(dmul(e1x, e2y), dmul(e1y, e2x));
-    const double span = fmax(fmax(fabs(e1x), fabs(e1y)), fmax(fabs(e2x), fabs(e2y)));
-    if (!(fabs(orient) > dmul(1e-12, fmax(dmul(span, span), 1e-300)))) continue;  // collinear or repeated sites
-    const double sgn = orient > 0.0 ? 1.0 : -1.0;
-    bool empty = true;
-    for (int d = 0; d < NS; ++d) {
-      if (d == i || d == j || d == k) continue;
-      const double px = sx[d], py = sy[d];
-      const double adx = dsub(ax, px), ady = dsub(ay, py);
-      const double bdx = dsub(bx, px), bdy = dsub(by, py);
-      const double cdx = dsub(cx, px), cdy = dsub(cy, py);
-      const double a2 = dadd(dmul(adx, adx), dmul(ady, ady));
-      const double b2 = dadd(dmul(bdx, bdx), dmul(bdy, bdy));
-      const double c2 = dadd(dmul(cdx, cdx), dmul(cdy, cdy));
-      const double t1 = dmul(adx, dsub(dmul(bdy, c2), dmul(b2, cdy)));
-      const double t2 = dmul(ady, dsub(dmul(bdx, c2), dmul(b2, cdx)));
-      const double t3 = dmul(a2, dsub(dmul(bdx, cdy), dmul(bdy, cdx)));
-      const double det = dmul(dadd(dsub(t1, t2), t3), sgn);  // > 0: site d strictly inside the circumcircle
-      const double mag = dadd(dadd(fabs(t1), fabs(t2)), fabs(t3));
-      if (det > dmul(INCIRCLE_TOL, mag)) { empty = false; break; }
-    }
-    if (empty) {
-      const int slot = atomicAdd(&counts[f], 1);
-      if (slot < MAXT) tris[(size_t)f * MAXT + slot] = TriRec{i, j, k, (i * NS + j) * NS + k};
-    }
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= NTRIPLES) return;
+  int lo = 0, hi = NS - 3;  // first index: the largest i with before[i] <= t
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (before[mid] <= t) lo = mid; else hi = mid - 1;
   }
+  const int i = lo, m = NS - 1 - i, r = t - before[i];  // r ranks the pair (jj < kk) among the m sites after i
+  const float b2m = (float)(2 * m - 1);
+  int jj = (int)((b2m - sqrtf(fmaxf(b2m * b2m - 8.f * (float)r, 0.f))) * 0.5f);
+  jj = max(0, min(jj, m - 2));
+  while ((jj + 1) * m - (jj + 1) * (jj + 2) / 2 <= r) ++jj;
+  while (jj * m - jj * (jj + 1) / 2 > r) --jj;
+  const int kk = r - (jj * m - jj * (jj + 1) / 2) + jj + 1;
+  const int j = i + 1 + jj, k = i + 1 + kk;
+  const double ax = sx[i], ay = sy[i], bx = sx[j], by = sy[j], cx = sx[k], cy = sy[k];
+  const double e1x = dsub(bx, ax), e1y = dsub(by, ay), e2x = dsub(cx, ax), e2y = dsub(cy, ay);
+  const double orient = dsub(dmul(e1x, e2y), dmul(e1y, e2x));
+  const double span = fmax(fmax(fabs(e1x), fabs(e1y)), fmax(fabs(e2x), fabs(e2y)));
+  if (!(fabs(orient) > dmul(1e-12, fmax(dmul(span, span), 1e-300)))) return;  // collinear or repeated sites
+  const double sgn = orient > 0.0 ? 1.0 : -1.0;
+  int d = i;
+  for (int s = 0; s < NS - 1; ++s) {
+    d = (d + 1 == NS) ? 0 : d + 1;
+    if (d == j || d == k) continue;
+    const double px = sx[d], py = sy[d];
+    const double adx = dsub(ax, px), ady = dsub(ay, py);
+    const double bdx = dsub(bx, px), bdy = dsub(by, py);
+    const double cdx = dsub(cx, px), cdy = dsub(cy, py);
+    const double a2 = dadd(dmul(adx, adx), dmul(ady, ady));
+    const double b2 = dadd(dmul(bdx, bdx), dmul(bdy, bdy));
+    const double c2 = dadd(dmul(cdx, cdx), dmul(cdy, cdy));
+    const double t1 = dmul(adx, dsub(dmul(bdy, c2), dmul(b2, cdy)));
+    const double t2 = dmul(ady, dsub(dmul(bdx, c2), dmul(b2, cdx)));
+    const double t3 = dmul(a2, dsub(dmul(bdx, cdy), dmul(bdy, cdx)));
+    const double det = dmul(dadd(dsub(t1, t2), t3), sgn);  // > 0: site d strictly inside the circumcircle
+    const double mag = dadd(dadd(fabs(t1), fabs(t2)), fabs(t3));
+    if (det > dmul(INCIRCLE_TOL, mag)) return;
+  }
+  const int slot = atomicAdd(&counts[f], 1);
+  if (slot < MAXT) tris[(size_t)f * MAXT + slot] = TriRec{i, j, k, (i * NS + j) * NS + k};
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -311,7 +329,7 @@ extern "C" int ap_cond_motion256(int device, int T, const float* lm_src, int src
   int* counts = (int*)workspace;
   TriRec* tris = (TriRec*)((char*)workspace + motion_counts_bytes(T));
   AP_CUDA(cudaMemsetAsync(counts, 0, (size_t)T * sizeof(int), st));
-  delaunay_kernel<<<dim3(NS - 2, T), 128, 0, st>>>(lm_dst, counts, tris);
+  delaunay_kernel<<<dim3((NTRIPLES + 127) / 128, T), 128, 0, st>>>(lm_dst, counts, tris);
   AP_CUDA(cudaGetLastError());
   motion_raster_kernel<<<dim3(256 / 32, 256 / 8, T), 256, 0, st>>>(lm_src, src_per_frame ? NLM * 2 : 0, lm_dst, counts, tris,
                                                                   motion);

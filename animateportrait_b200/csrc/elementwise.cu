@@ -339,17 +339,18 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpP p) {
   // ---- per-thread channel quad: mean / rstd of the producer's InstanceNorm ----
   const int cq = tid % TPP, py = tid / TPP;
   const int c = cq * 4;
+  const int ns = p.src_shared ? 0 : n;  // clip mode: every frame warps the same photo features
   float mean[4], rstd[4];
   {
     const double inv_n = 1.0 / (double)(S * S);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
+    for (int e = 0; e < 4; ++e) stats_to_affine(p.stats, ns, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
   }
   __syncthreads();
 
   // ---- phase 2: gather ----
   constexpr int NY = 256 / TPP;
-  const float* src = p.raw + (size_t)n * S * S * p.raw_C + p.raw_coff + c;
+  const float* src = p.raw + (size_t)ns * S * S * p.raw_C + p.raw_coff + c;
   const int logS = 31 - __clz(S);
   Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, S, S, 0};
 #pragma unroll 1

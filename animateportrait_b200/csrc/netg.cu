@@ -86,6 +86,9 @@ struct TapRec {
 
 struct Plan {
   int B = 0;
+  // clip mode: ONE photo shared by all B frames.  Everything that depends on the photo alone (the three stems, tri11,
+  // tri21, tri22 and their InstanceNorms) is computed for a batch of 1 and the warps read it for every frame.
+  bool shared_photo = false;
   char* arena = nullptr;
   size_t arena_bytes = 0;
   char* sarena = nullptr;  // InstanceNorm statistics, zeroed at the start of every forward
@@ -412,7 +415,8 @@ struct Runner {
     p.raw = r.p; p.raw_C = r.C; p.raw_coff = rcoff;
     p.stats = r.stats; p.stat_C = r.C; p.stat_coff = rcoff;
     p.motion = in.motion; p.flow = in.flow; p.ifmask = in.ifmask;
-    p.B = r.B; p.S = r.H; p.C = C; p.level = level;
+    p.B = pl->B; p.S = r.H; p.C = C; p.level = level;
+    p.src_shared = (r.B == 1 && pl->B > 1) ? 1 : 0;  // clip mode: one photo's features, warped per frame
     p.fmt = dst.fmt; p.d0 = dst.p0; p.d1 = dst.p1; p.dC = dst.C; p.dcoff = dcoff; p.dpad = dst.pad;
     AP_TRY(launch_warp(p, st));
     return mark(CL_WARP, 0.0);
@@ -444,6 +448,7 @@ static ConvGeom geom_convT_phase(int B, int Hin, int Cin, int Cout, int py, int 
 
 int Runner::run(const Inputs& in) {
   const int B = pl->B;
+  const int Bp = pl->shared_photo ? 1 : B;  // batch of the photo-only part of the encoder
   const int prec = h->prec;
   const int afmt = (prec == AP_PREC_FP32X3) ? FMT_BF16X2 : (prec == AP_PREC_BF16 ? FMT_BF16 : FMT_F32);
   const int hp = (prec == AP_PREC_FP32_SIMT) ? 0 : 1;  // halo of reflect-padded tensor-core inputs
@@ -502,13 +507,13 @@ int Runner::run(const Inputs& in) {
   }
 
   // ---- three 7x7 stems fused into one Cout=160 problem on the photo (networks.py:1218-1243) ----
-  Raw stem = raw(B, 256, 256, 160, true);
+  Raw stem = raw(Bp, 256, 256, 160, true);
   AP_TRY(wait_input(0));
   if (prec == AP_PREC_FP32_SIMT) {
-    AP_TRY(conv_thin(geom_conv(B, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
+    AP_TRY(conv_thin(geom_conv(Bp, 256, 3, 160, 7, 1, 3, 1), in.input, 1, 3, h->w_stem, stem));
   } else if (ph == PH_EXEC) {
-    AP_TRY(launch_stem_umma(in.input, h->w_stem_img, stem.p, stem.stats, B, prec == AP_PREC_FP32X3 ? 3 : 1, st));
-    AP_TRY(mark(CL_STEM, 2.0 * B * 65536.0 * 147 * 160));
+    AP_TRY(launch_stem_umma(in.input, h->w_stem_img, stem.p, stem.stats, Bp, prec == AP_PREC_FP32X3 ? 3 : 1, st));
+    AP_TRY(mark(CL_STEM, 2.0 * Bp * 65536.0 * 147 * 160));
   }
   tap_raw("tri00", stem, 0, 32, 1);
   tap_raw("tri10", stem, 32, 64, 1);
@@ -534,13 +539,13 @@ int Runner::run(const Inputs& in) {
 
   // ---- stems of branches 2 and 3, normalised once: T12 = [tri10 | tri20] (side stream 1) ----
   on(s1);
-  Act T12 = act(B, 256, 256, 128, 0, afmt);
+  Act T12 = act(Bp, 256, 256, 128, 0, afmt);
   AP_TRY(apply(stem, 32, 128, 1, &T12, 0, 0));
   AP_TRY(order_after(s2, s1));
 
   // ---- branch 2 (side stream 1): tri11 -> warp L1 -> tri12 ----
-  Raw r11 = raw(B, 128, 128, 64, true);
-  AP_TRY(conv(geom_conv(B, 256, 64, 64, 3, 2, 1, 0), T12, 0, W("model_tri11.0"), r11, 0));
+  Raw r11 = raw(Bp, 128, 128, 64, true);
+  AP_TRY(conv(geom_conv(Bp, 256, 64, 64, 3, 2, 1, 0), T12, 0, W("model_tri11.0"), r11, 0));
   tap_raw("tri11", r11, 0, 64, 1);
   Act W1 = act(B, 128, 128, 128, 0, afmt);
   AP_TRY(wait_input(1));
@@ -553,13 +558,13 @@ int Runner::run(const Inputs& in) {
 
   // ---- branch 3 (side stream 2): tri21 -> tri22 -> warp L2 ----
   on(s2);
-  Raw r21 = raw(B, 128, 128, 128, true);
-  AP_TRY(conv(geom_conv(B, 256, 64, 128, 3, 2, 1, 0), T12, 64, W("model_tri21.0"), r21, 0));
+  Raw r21 = raw(Bp, 128, 128, 128, true);
+  AP_TRY(conv(geom_conv(Bp, 256, 64, 128, 3, 2, 1, 0), T12, 64, W("model_tri21.0"), r21, 0));
   tap_raw("tri21", r21, 0, 128, 1);
-  Act A21 = act(B, 128, 128, 128, 0, afmt);
+  Act A21 = act(Bp, 128, 128, 128, 0, afmt);
   AP_TRY(apply(r21, 0, 128, 1, &A21, 0, 0));
-  Raw r22 = raw(B, 64, 64, 128, true);
-  AP_TRY(conv(geom_conv(B, 128, 128, 128, 3, 2, 1, 0), A21, 0, W("model_tri22.0"), r22, 0));
+  Raw r22 = raw(Bp, 64, 64, 128, true);
+  AP_TRY(conv(geom_conv(Bp, 128, 128, 128, 3, 2, 1, 0), A21, 0, W("model_tri22.0"), r22, 0));
   tap_raw("tri22", r22, 0, 128, 1);
   AP_TRY(wait_input(1));
   AP_TRY(warp(r22, 0, 128, 2, in, MI, 512));
@@ -687,11 +692,13 @@ int Runner::run(const Inputs& in) {
   return AP_OK;
 }
 
-static int get_plan(ap_netg* h, int B, Plan** out) {
-  auto it = h->plans.find(B);
+static int get_plan(ap_netg* h, int B, bool shared_photo, Plan** out) {
+  const int key = B * 2 + (shared_photo ? 1 : 0);
+  auto it = h->plans.find(key);
   if (it != h->plans.end()) { *out = it->second; return AP_OK; }
   Plan* pl = new Plan();
   pl->B = B;
+  pl->shared_photo = shared_photo;
   Inputs none{};
   Runner rs{h, pl, PH_SIZE, nullptr};
   int rc = rs.run(none);
@@ -715,7 +722,7 @@ static int get_plan(ap_netg* h, int B, Plan** out) {
       delete pl;
       return AP_ERR_CUDA;
     }
-  h->plans[B] = pl;
+  h->plans[key] = pl;
   *out = pl;
   return AP_OK;
 }
@@ -915,9 +922,10 @@ int ap_netg_workspace_bytes(ap_netg* h, int B, size_t* bytes) {
   return AP_OK;
 }
 
-static int forward_impl(ap_netg* h, int B, const Inputs& in, cudaStream_t st, const cudaEvent_t* in_ready) {
+static int forward_impl(ap_netg* h, int B, const Inputs& in, cudaStream_t st, const cudaEvent_t* in_ready,
+                        bool shared_photo = false) {
   Plan* pl = nullptr;
-  AP_TRY(get_plan(h, B, &pl));
+  AP_TRY(get_plan(h, B, shared_photo, &pl));
   const int64_t before = launches_get();
   Runner rx{h, pl, PH_EXEC, st};
   rx.in_ready = in_ready;
@@ -949,13 +957,25 @@ int ap_netg_forward(ap_netg* h, int B, const float* input, const float* land1, c
   return forward_impl(h, B, in, (cudaStream_t)cuda_stream, nullptr);
 }
 
+int ap_netg_forward_shared_photo(ap_netg* h, int B, const float* input, const float* land1, const float* land2,
+                                 const float* motion, const float* flow, const float* ifmask, float* out,
+                                 void* cuda_stream) {
+  AP_REQUIRE(h != nullptr, AP_ERR_INVALID, "null handle");
+  AP_REQUIRE(h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1, AP_ERR_INVALID, "B=%d", B);
+  AP_REQUIRE(input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "null tensor pointer");
+  AP_CUDA(cudaSetDevice(h->device));
+  Inputs in{input, land1, land2, motion, flow, ifmask, out};
+  return forward_impl(h, B, in, (cudaStream_t)cuda_stream, nullptr, true);
+}
+
 int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* land1, const float* land2,
                          const float* motion, const float* flow, const float* ifmask, float* out, void* cuda_stream) {
   AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
   AP_REQUIRE(B >= 1 && input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "bad argument");
   AP_CUDA(cudaSetDevice(h->device));
   Plan* pl = nullptr;
-  AP_TRY(get_plan(h, B, &pl));
+  AP_TRY(get_plan(h, B, false, &pl));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const size_t px = (size_t)B * 256 * 256;
   const size_t sz[6] = {px * 3, px, px, px * 2, px * 2, px};

@@ -187,6 +187,31 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
         return out
 
     @torch.no_grad()
+    def forward_shared_photo(self, input, land1, land2, motion, flow, ifmask):
+        """Clip form of forward(): `input` is ONE photo [1,3,256,256] shared by the B frames the other five tensors
+        describe (`ap_netg_forward_shared_photo`): the photo-only part of the encoder runs once per call.  Same result as
+        forward(input.expand(B, ...), ...)."""
+        if not input.is_cuda:
+            raise RuntimeError("the B200 generator runs on CUDA tensors only (no CPU fallback)")
+        dev = input.device
+        B = land2.shape[0]
+        want = {"input": (1, 3, 256, 256), "land1": (B, 1, 256, 256), "land2": (B, 1, 256, 256),
+                "motion": (B, 256, 256, 2), "flow": (B, 2, 256, 256), "ifmask": (B, 1, 256, 256)}
+        ts = []
+        for (name, shape), t in zip(want.items(), (input, land1, land2, motion, flow, ifmask)):
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+            ts.append(t.detach().to(device=dev, dtype=torch.float32).contiguous())
+        with torch.cuda.device(dev):
+            self._sync(dev)
+            out = torch.empty((B, self.output_nc, 256, 256), device=dev, dtype=torch.float32)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib().ap_netg_forward_shared_photo(self._handle, B, *[C.c_void_p(t.data_ptr()) for t in ts],
+                                                                 C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
+                        "ap_netg_forward_shared_photo")
+        return out
+
+    @torch.no_grad()
     def forward_host(self, input, land1, land2, motion, flow, ifmask, device: Optional[torch.device] = None,
                      out: Optional[torch.Tensor] = None):
         """End-to-end form: CPU tensors in (pinned for full copy speed), CPU frames out.

@@ -135,7 +135,7 @@ def run_reference(args, rank):
 
 
 CLIP_METRIC_NOTE = ("configs[2]: one photo + {T} target landmark sets (12 s clip), landmark maps + Delaunay motion field on the "
-                    "GPU, netG output_nc={onc} precision={prec} in batches of {B}, blend with the static drawing, uint8 frames; "
+                    "GPU, netG output_nc={onc} precision={prec} in batches of {B}{share}, blend with the static drawing, uint8 frames; "
                     "intrinsic flow / visibility mask are device-resident stand-ins for netF's output (not built)")
 
 
@@ -198,7 +198,7 @@ def run_reference_clip(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CLIP_METRIC_NOTE.format(T=args.frames, onc=args.output_nc, prec="fp32 (CPU)", B=1)
+            "config": {"workload": CLIP_METRIC_NOTE.format(T=args.frames, onc=args.output_nc, prec="fp32 (CPU)", B=1, share="")
                        + f"; step = {n}-frame sample of the clip"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -233,7 +233,7 @@ def run_clip(args, rank, local_rank, world):
     flow_d, ifm_d = flow[lo:hi].to(dev), ifmask[lo:hi].to(dev)
     seq_host = seq.pin_memory()
     seq_dev = seq.to(dev) if rank == 0 else None
-    r = ClipRenderer(net, batch=B)
+    r = ClipRenderer(net, batch=B, share_photo=not args.no_share_photo)
     r.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
     mine = torch.empty((hi - lo, 256, 256, 3), dtype=torch.uint8, device=dev)
     frames_host = torch.empty((T, 256, 256, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
@@ -314,7 +314,10 @@ def run_clip(args, rank, local_rank, world):
     prof = None
     with torch.no_grad():
         for _ in range(3):
-            net(photo_b, land1_b, land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
+            if args.no_share_photo:
+                net(photo_b, land1_b, land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
+            else:
+                net.forward_shared_photo(photo_b[:1], land1_b, land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
             p = net.get_profile()
             if prof is None:
                 prof = p
@@ -355,7 +358,9 @@ def run_clip(args, rank, local_rank, world):
                 "dtype": {"fp32": "bf16x3 (hi/lo split, fp32 accumulate; fp32-accurate)", "bf16": "bf16",
                           "fp32_simt": "f32"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": CLIP_METRIC_NOTE.format(T=T, onc=onc, prec=args.precision, B=B),
+                "config": {"workload": CLIP_METRIC_NOTE.format(T=T, onc=onc, prec=args.precision, B=B,
+                                                               share=" (photo-only encoder layers once per batch)"
+                                                               if not args.no_share_photo else " (B copies of the photo)"),
                            "l2": f"every batch touches a {net.workspace_bytes(min(B, T)) / 1e9:.1f} GB working set (> 126 MB L2); "
                                  "per-frame inputs differ for every frame of the clip",
                            "parallelism": f"dp{world} (frames of one clip sharded; landmark scatter + frame gather only)"},
@@ -380,6 +385,8 @@ def main():
     ap_.add_argument("--batch", type=int, default=None)
     ap_.add_argument("--output-nc", type=int, default=1, dest="output_nc")
     ap_.add_argument("--no-cpu-baseline", action="store_true")
+    ap_.add_argument("--no-share-photo", action="store_true",
+                     help="clip workload: hand netG B copies of the photo instead of the shared-photo entry point")
     args = ap_.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     clip = args.workload == "clip"

@@ -119,3 +119,34 @@ def test_clip_renderer_matches_frame_by_frame_oracle(onc):
     motion = torch.from_numpy(OC.cal_motion(src.numpy(), seq[0].numpy()))[None]
     ref = O.netg_forward(sd, photo, land1, land2, motion, torch.zeros(1, 2, 256, 256), torch.ones(1, 1, 256, 256))
     assert (plain - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp32_simt"])
+def test_shared_photo_forward_equals_forward_on_copies_of_the_photo(precision):
+    """ap_netg_forward_shared_photo == ap_netg_forward on B copies of the photo: the same kernels on the same numbers,
+    only the InstanceNorm statistics of the photo-only layers are accumulated once instead of B times."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import animateportrait_b200 as ap
+    dev = torch.device("cuda", 0)
+    B = 5
+    net = ap.define_G(3, 1, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3,
+                      precision=precision).module
+    net.load_state_dict(synth.make_state_dict(1, seed=4, bias_std=0.2))
+    x, l1, l2, motion, flow, ifm = (t.to(dev) for t in synth.make_inputs(B, seed=77, kind="smooth"))
+    photo = x[:1].contiguous()
+    with torch.no_grad():
+        want = net(photo.expand(B, 3, 256, 256).contiguous(), l1, l2, motion, flow, ifm)
+        got = net.forward_shared_photo(photo, l1, l2, motion, flow, ifm)
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= (2e-2 if precision == "bf16" else 2e-5)
+        for tap in ("tri00", "tri11", "tri22"):                     # photo-only taps are a batch of one in clip mode
+            assert net.debug_read(tap).shape[0] == 1
+        assert net.debug_read("warp2").shape[0] == B
+        # B = 1 and a second batch size reuse nothing stale
+        one = net.forward_shared_photo(photo, l1[:1], l2[:1], motion[:1], flow[:1], ifm[:1])
+        assert (one - want[:1]).abs().max().item() <= (2e-2 if precision == "bf16" else 2e-5)
+    with pytest.raises(RuntimeError, match="input"):
+        net.forward_shared_photo(x, l1, l2, motion, flow, ifm)
