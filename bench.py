@@ -395,7 +395,7 @@ def main():
     if args.precision is None:
         args.precision = "bf16" if clip else "fp32"      # configs[2] is quoted on bf16 convs, configs[1] on fp32
     if args.batch is None:
-        args.batch = 32 if clip else 16
+        args.batch = 64 if clip else 16
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

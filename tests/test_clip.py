@@ -125,8 +125,10 @@ def test_clip_renderer_matches_frame_by_frame_oracle(onc):
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp32_simt"])
 def test_shared_photo_forward_equals_forward_on_copies_of_the_photo(precision):
-    """ap_netg_forward_shared_photo == ap_netg_forward on B copies of the photo: the same kernels on the same numbers,
-    only the InstanceNorm statistics of the photo-only layers are accumulated once instead of B times."""
+    """ap_netg_forward_shared_photo == ap_netg_forward on B copies of the photo: the same kernels on the same numbers;
+    only the summation order of the InstanceNorm statistics of the photo-only layers differs (tile -> CTA assignment
+    changes with the batch size), which the network amplifies to <= 2e-4 -- the same bound tests/test_gpu_parity.py
+    puts on two runs of the same call (measured 7.5e-5)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import animateportrait_b200 as ap
@@ -141,12 +143,12 @@ def test_shared_photo_forward_equals_forward_on_copies_of_the_photo(precision):
         want = net(photo.expand(B, 3, 256, 256).contiguous(), l1, l2, motion, flow, ifm)
         got = net.forward_shared_photo(photo, l1, l2, motion, flow, ifm)
         assert got.shape == want.shape
-        assert (got - want).abs().max().item() <= (2e-2 if precision == "bf16" else 2e-5)
+        assert (got - want).abs().max().item() <= (2e-2 if precision == "bf16" else 2e-4)
         for tap in ("tri00", "tri11", "tri22"):                     # photo-only taps are a batch of one in clip mode
             assert net.debug_read(tap).shape[0] == 1
         assert net.debug_read("warp2").shape[0] == B
         # B = 1 and a second batch size reuse nothing stale
         one = net.forward_shared_photo(photo, l1[:1], l2[:1], motion[:1], flow[:1], ifm[:1])
-        assert (one - want[:1]).abs().max().item() <= (2e-2 if precision == "bf16" else 2e-5)
+        assert (one - want[:1]).abs().max().item() <= (2e-2 if precision == "bf16" else 2e-4)
     with pytest.raises(RuntimeError, match="input"):
         net.forward_shared_photo(x, l1, l2, motion, flow, ifm)
