@@ -60,13 +60,34 @@ __device__ __forceinline__ int triples_before(int i) {  // triples whose first i
   return NTRIPLES - r * (r - 1) * (r - 2) / 6;
 }
 
+// fp32 screen of the in-circle determinant: +1 = certainly inside, -1 = certainly outside, 0 = too close to call (the
+// caller repeats the test in fp64).  M bounds every product that enters the determinant, so the fp32 rounding error of
+// `det` is below ~1e-6 * M; a margin of 1e-5 * M therefore never contradicts the fp64 decision det64 > 1e-9 * mag64
+// (mag64 <= M).  The fp64 pipe was the bound of this kernel (73 % active, profiles/r01_run11_cond_ncu.txt): with the
+// screen it only sees nearly co-circular quadruples.
+__device__ __forceinline__ int incircle_screen(float ax, float ay, float bx, float by, float cx, float cy, float px,
+                                               float py, float sgn) {
+  const float adx = ax - px, ady = ay - py, bdx = bx - px, bdy = by - py, cdx = cx - px, cdy = cy - py;
+  const float a2 = adx * adx + ady * ady, b2 = bdx * bdx + bdy * bdy, c2 = cdx * cdx + cdy * cdy;
+  const float u1 = bdy * c2, u2 = b2 * cdy, u3 = bdx * c2, u4 = b2 * cdx, u5 = bdx * cdy, u6 = bdy * cdx;
+  const float det = (adx * (u1 - u2) - ady * (u3 - u4) + a2 * (u5 - u6)) * sgn;
+  const float M = fabsf(adx) * (fabsf(u1) + fabsf(u2)) + fabsf(ady) * (fabsf(u3) + fabsf(u4)) + a2 * (fabsf(u5) + fabsf(u6));
+  const float thr = 1e-5f * M;
+  return det > thr ? 1 : (det < -thr ? -1 : 0);
+}
+
 __global__ void __launch_bounds__(128) delaunay_kernel(const float* __restrict__ lm_dst, int* __restrict__ counts,
                                                        TriRec* __restrict__ tris) {
   __shared__ double sx[NS], sy[NS];
+  __shared__ float fx[NS], fy[NS];
   __shared__ int before[NS];
   const int f = blockIdx.y;
   load_sites(lm_dst + (size_t)f * NLM * 2, sx, sy);
-  if (threadIdx.x < NS) before[threadIdx.x] = triples_before(threadIdx.x);
+  if (threadIdx.x < NS) {
+    before[threadIdx.x] = triples_before(threadIdx.x);
+    fx[threadIdx.x] = (float)sx[threadIdx.x];  // exact: the sites are float32 values (or the corners 0 / 255)
+    fy[threadIdx.x] = (float)sy[threadIdx.x];
+  }
   __syncthreads();
   const int t = blockIdx.x * 128 + threadIdx.x;
   if (t >= NTRIPLES) return;
@@ -89,10 +110,14 @@ __global__ void __launch_bounds__(128) delaunay_kernel(const float* __restrict__
   const double span = fmax(fmax(fabs(e1x), fabs(e1y)), fmax(fabs(e2x), fabs(e2y)));
   if (!(fabs(orient) > dmul(1e-12, fmax(dmul(span, span), 1e-300)))) return;  // collinear or repeated sites
   const double sgn = orient > 0.0 ? 1.0 : -1.0;
+  const float fax = fx[i], fay = fy[i], fbx = fx[j], fby = fy[j], fcx = fx[k], fcy = fy[k], fsgn = (float)sgn;
   int d = i;
   for (int s = 0; s < NS - 1; ++s) {
     d = (d + 1 == NS) ? 0 : d + 1;
     if (d == j || d == k) continue;
+    const int screen = incircle_screen(fax, fay, fbx, fby, fcx, fcy, fx[d], fy[d], fsgn);
+    if (screen > 0) return;
+    if (screen < 0) continue;
     const double px = sx[d], py = sy[d];
     const double adx = dsub(ax, px), ady = dsub(ay, py);
     const double bdx = dsub(bx, px), bdy = dsub(by, py);

@@ -37,7 +37,11 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
 // stream;  3: + residual read from the block's input activation (fp32, or bf16 hi + lo = 16 mantissa bits).
 // 85 registers at most (3 CTAs = 24 warps per SM, each thread with 4-12 independent 16-byte loads in flight) and
 // CTAs of only 8 pixel passes, so that the grid is several balanced waves instead of 1.7 fat ones.
-template <int TPP, int MODE>
+// UNROLL = pixel passes whose loads are in flight together.  4: two rounds per CTA.  8 (MODE 0 only, "deep"): the whole
+// CTA's 8 passes are issued before anything else, and the statistics are finalised UNDER those loads -- a MODE 0 CTA
+// moves half the bytes of a MODE 1/2 one at the same latency chain (stats -> round 1 -> round 2), which left it at
+// 3.6 TB/s where the two-operand modes reach 5-6.6 TB/s (profiles/r01_run11_clip_launches.txt).
+template <int TPP, int MODE, int UNROLL>
 __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   constexpr int NY = 256 / TPP;  // pixels per pass
   constexpr int APPLY_PIX_PER_CTA = 8 * NY;
@@ -46,8 +50,8 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   const int c = cq * 4;
   const int HW = p.H * p.W;
   const int logW = 31 - __clz(p.W);
-  float mean[4], rstd[4], mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {0.f, 0.f, 0.f, 0.f};
-  {
+  float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {0.f, 0.f, 0.f, 0.f};
+  auto finalise_stats = [&]() {
     const double inv_n = 1.0 / (double)HW;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -55,7 +59,8 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
       else { mean[e] = p.bias ? -p.bias[c + e] : 0.f; rstd[e] = 1.f; }
       if (MODE == 1) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
     }
-  }
+  };
+  if (UNROLL != 8) finalise_stats();
   Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
   const int pix0 = blockIdx.x * APPLY_PIX_PER_CTA + py;
   const float* raw = p.raw + ((size_t)n * HW) * p.raw_C + p.raw_coff + c;
@@ -65,10 +70,10 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   const int rWp = p.W + 2 * p.res_pad;
   const size_t rbase = (size_t)n * (p.H + 2 * p.res_pad);
 #pragma unroll 1
-  for (int k0 = 0; k0 < APPLY_PIX_PER_CTA; k0 += 4 * NY) {
-    float4 v[4], u[4];
+  for (int k0 = 0; k0 < APPLY_PIX_PER_CTA; k0 += UNROLL * NY) {
+    float4 v[UNROLL], u[UNROLL];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < UNROLL; ++j) {
       const int pix = pix0 + k0 + j * NY;
       v[j] = p.l2_hints ? ld_stream_evict_first(raw + (size_t)pix * p.raw_C) : ld_stream(raw + (size_t)pix * p.raw_C);
       if (MODE == 1) u[j] = p.l2_hints ? ld_stream_evict_first(raw2 + (size_t)pix * p.raw2_C) : ld_stream(raw2 + (size_t)pix * p.raw2_C);
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
         }
       }
     }
+    if (UNROLL == 8) finalise_stats();  // one round per CTA: the statistics' latency hides under the data loads
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < UNROLL; ++j) {
       const int pix = pix0 + k0 + j * NY;
       float4 o;
       o.x = (v[j].x - mean[0]) * rstd[0];
@@ -182,20 +188,24 @@ static void prefer_max_shared(K kernel) {
 
 template <int TPP>
 static void apply_carveouts() {
-  prefer_max_shared(apply_kernel<TPP, 0>);
-  prefer_max_shared(apply_kernel<TPP, 1>);
-  prefer_max_shared(apply_kernel<TPP, 2>);
-  prefer_max_shared(apply_kernel<TPP, 3>);
+  prefer_max_shared(apply_kernel<TPP, 0, 4>);
+  prefer_max_shared(apply_kernel<TPP, 0, 8>);
+  prefer_max_shared(apply_kernel<TPP, 1, 4>);
+  prefer_max_shared(apply_kernel<TPP, 2, 4>);
+  prefer_max_shared(apply_kernel<TPP, 3, 4>);
 }
 
 template <int TPP>
 static void launch_apply_tpp(const ApplyP& p, dim3 grid, cudaStream_t st) {
   static bool once = false;
   if (!once) { apply_carveouts<TPP>(); once = true; }
-  if (p.raw2) apply_kernel<TPP, 1><<<grid, 256, 0, st>>>(p);
-  else if (p.res_in) apply_kernel<TPP, 2><<<grid, 256, 0, st>>>(p);
-  else if (p.res_fmt >= 0) apply_kernel<TPP, 3><<<grid, 256, 0, st>>>(p);
-  else apply_kernel<TPP, 0><<<grid, 256, 0, st>>>(p);
+  static int deep = -1;  // AP_NETG_APPLY_DEEP=0: the two-round MODE 0 kernel (A/B)
+  if (deep < 0) { const char* e = getenv("AP_NETG_APPLY_DEEP"); deep = !(e && e[0] == '0'); }
+  if (p.raw2) apply_kernel<TPP, 1, 4><<<grid, 256, 0, st>>>(p);
+  else if (p.res_in) apply_kernel<TPP, 2, 4><<<grid, 256, 0, st>>>(p);
+  else if (p.res_fmt >= 0) apply_kernel<TPP, 3, 4><<<grid, 256, 0, st>>>(p);
+  else if (deep) apply_kernel<TPP, 0, 8><<<grid, 256, 0, st>>>(p);
+  else apply_kernel<TPP, 0, 4><<<grid, 256, 0, st>>>(p);
 }
 
 static int g_apply_hints = -1;

@@ -84,11 +84,14 @@ struct TapRec {
   const double* stats; int stat_C, stat_coff; int relu;
 };
 
+constexpr size_t AP_MAX_PLANS = 6;
+
 struct Plan {
   int B = 0;
   // clip mode: ONE photo shared by all B frames.  Everything that depends on the photo alone (the three stems, tri11,
   // tri21, tri22 and their InstanceNorms) is computed for a batch of 1 and the warps read it for every frame.
   bool shared_photo = false;
+  uint64_t last_use = 0;  // plan cache is LRU-bounded (AP_MAX_PLANS): ragged tail batches of clips must not pile up arenas
   char* arena = nullptr;
   size_t arena_bytes = 0;
   char* sarena = nullptr;  // InstanceNorm statistics, zeroed at the start of every forward
@@ -187,7 +190,8 @@ struct ap_netg {
   float* b_merge = nullptr;  // [256]
   float* b_out = nullptr;    // [onc]
   std::vector<void*> owned;  // every device allocation holding weights
-  std::map<int, Plan*> plans;
+  std::map<int, Plan*> plans;  // key = 2 * B + shared_photo
+  uint64_t use_clock = 0;
   Plan* last_plan = nullptr;
   int64_t last_launches = 0;
 };
@@ -695,7 +699,18 @@ int Runner::run(const Inputs& in) {
 static int get_plan(ap_netg* h, int B, bool shared_photo, Plan** out) {
   const int key = B * 2 + (shared_photo ? 1 : 0);
   auto it = h->plans.find(key);
-  if (it != h->plans.end()) { *out = it->second; return AP_OK; }
+  if (it != h->plans.end()) { it->second->last_use = ++h->use_clock; *out = it->second; return AP_OK; }
+  // every plan owns a workspace arena (0.36 GB per frame of batch in the fp32-accurate mode): keep the most recently
+  // used AP_MAX_PLANS batch shapes.  Eviction frees device memory, so it waits for the device first.
+  while (h->plans.size() >= AP_MAX_PLANS) {
+    auto victim = h->plans.end();
+    for (auto p = h->plans.begin(); p != h->plans.end(); ++p)
+      if (victim == h->plans.end() || p->second->last_use < victim->second->last_use) victim = p;
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("device synchronisation before plan eviction failed"); return AP_ERR_CUDA; }
+    if (h->last_plan == victim->second) h->last_plan = nullptr;
+    delete victim->second;
+    h->plans.erase(victim);
+  }
   Plan* pl = new Plan();
   pl->B = B;
   pl->shared_photo = shared_photo;
@@ -722,6 +737,7 @@ static int get_plan(ap_netg* h, int B, bool shared_photo, Plan** out) {
       delete pl;
       return AP_ERR_CUDA;
     }
+  pl->last_use = ++h->use_clock;
   h->plans[key] = pl;
   *out = pl;
   return AP_OK;

@@ -204,3 +204,26 @@ def test_branch_overlap_on_side_streams_matches_serial_execution(dev, monkeypatc
     assert (outs["1"] - outs["0"]).abs().max().item() <= 2e-4
     y_ref = O.netg_forward(sd, *[t[1:2].cpu() for t in inputs])
     assert (outs["1"][1:2].cpu() - y_ref).abs().max().item() <= FP32_TOL
+
+
+def test_plan_cache_is_bounded_and_eviction_is_transparent(dev):
+    """The library keeps the workspaces of the 6 most recently used batch shapes (csrc/netg.cu: AP_MAX_PLANS); going
+    through more shapes than that evicts the oldest and re-plans it on the next use with the same results."""
+    sd = O.make_state_dict(1, seed=12)
+    inputs = [t.to(dev) for t in O.make_inputs(8, seed=77, kind="smooth")]
+    net = _net(1, sd, dev, "fp32").module
+    with torch.no_grad():
+        first = net(*inputs).clone()                 # B=8: the largest arena, planned first
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info(dev)[0]
+        for b in range(7, 0, -1):                    # 7 more shapes: B=8 and B=7 get evicted
+            y = net(*[t[:b] for t in inputs])
+            assert (y - first[:b]).abs().max().item() <= 2e-4
+        torch.cuda.synchronize()
+        grown = free0 - torch.cuda.mem_get_info(dev)[0]
+        kept = sum(net.workspace_bytes(b) for b in range(1, 7))
+        # without eviction the library would now hold B=1..7 on top of B=8; with it B=8 (counted in free0) and B=7 are gone
+        assert grown < kept - net.workspace_bytes(8) + (1 << 30), (grown, kept)
+        again = net(*inputs)                         # re-planned
+        assert (again - first).abs().max().item() <= 2e-4
+        assert net.debug_read("merge").shape[0] == 8
