@@ -48,9 +48,7 @@ __device__ __forceinline__ void load_sites(const float* lm, double* sx, double* 
 // ------------------------------------------------------------------------------------------------------------------
 // Delaunay by exhaustion: one thread per site triple i < j < k (C(72,3) = 59,640 per frame, unranked from the flat thread
 // index so that every CTA carries the same work); the triple is kept when no other site lies strictly inside its
-// circumcircle.  The in-circle scan starts at the site after i -- landmark indices are spatially coherent, so a
-// neighbour of a vertex is the likeliest site inside a large circle and most triples are rejected after one or two
-// determinants.  In general position the survivors are THE Delaunay triangulation (2n-2-h triangles); co-circular sites
+// circumcircle.  In general position the survivors are THE Delaunay triangulation (2n-2-h triangles); co-circular sites
 // keep every triangulation of their cell, the rasteriser then picks by smallest key.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int NTRIPLES = NS * (NS - 1) * (NS - 2) / 6;
@@ -76,11 +74,35 @@ __device__ __forceinline__ int incircle_screen(float ax, float ay, float bx, flo
   return det > thr ? 1 : (det < -thr ? -1 : 0);
 }
 
+// exact in-circle decision of the oracle (float64, its op order): site p strictly inside the circumcircle of (a, b, c)
+__device__ __forceinline__ bool incircle_exact(double ax, double ay, double bx, double by, double cx, double cy, double px,
+                                               double py, double sgn) {
+  const double adx = dsub(ax, px), ady = dsub(ay, py);
+  const double bdx = dsub(bx, px), bdy = dsub(by, py);
+  const double cdx = dsub(cx, px), cdy = dsub(cy, py);
+  const double a2 = dadd(dmul(adx, adx), dmul(ady, ady));
+  const double b2 = dadd(dmul(bdx, bdx), dmul(bdy, bdy));
+  const double c2 = dadd(dmul(cdx, cdx), dmul(cdy, cdy));
+  const double t1 = dmul(adx, dsub(dmul(bdy, c2), dmul(b2, cdy)));
+  const double t2 = dmul(ady, dsub(dmul(bdx, c2), dmul(b2, cdx)));
+  const double t3 = dmul(a2, dsub(dmul(bdx, cdy), dmul(bdy, cdx)));
+  const double det = dmul(dadd(dsub(t1, t2), t3), sgn);
+  const double mag = dadd(dadd(fabs(t1), fabs(t2)), fabs(t3));
+  return det > dmul(INCIRCLE_TOL, mag);
+}
+
+// Two phases per CTA of 128 triples.  A: every thread tests its triple against the <= 12 index-neighbours (+-1, +-2) of
+// its three vertices -- landmark indices run along facial contours, so these are the sites most likely to sit inside the
+// circumcircle: 99 % of the triples are rejected here after 2 tests on average, and no lane waits long for another.
+// B: the few survivors are queued in shared memory and each is checked against ALL sites by a whole warp, one site per
+// lane (a serial scan per thread left 12 of 32 lanes active on average: profiles/r01_run11_cond_ncu.txt).
 __global__ void __launch_bounds__(128) delaunay_kernel(const float* __restrict__ lm_dst, int* __restrict__ counts,
                                                        TriRec* __restrict__ tris) {
   __shared__ double sx[NS], sy[NS];
   __shared__ float fx[NS], fy[NS];
   __shared__ int before[NS];
+  __shared__ TriRec queue[128];  // key field: orientation sign of the triple
+  __shared__ int n_queue;
   const int f = blockIdx.y;
   load_sites(lm_dst + (size_t)f * NLM * 2, sx, sy);
   if (threadIdx.x < NS) {
@@ -88,52 +110,59 @@ __global__ void __launch_bounds__(128) delaunay_kernel(const float* __restrict__
     fx[threadIdx.x] = (float)sx[threadIdx.x];  // exact: the sites are float32 values (or the corners 0 / 255)
     fy[threadIdx.x] = (float)sy[threadIdx.x];
   }
+  if (threadIdx.x == 0) n_queue = 0;
   __syncthreads();
   const int t = blockIdx.x * 128 + threadIdx.x;
-  if (t >= NTRIPLES) return;
-  int lo = 0, hi = NS - 3;  // first index: the largest i with before[i] <= t
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (before[mid] <= t) lo = mid; else hi = mid - 1;
+  if (t < NTRIPLES) {
+    int lo = 0, hi = NS - 3;  // first index: the largest i with before[i] <= t
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (before[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int i = lo, m = NS - 1 - i, r = t - before[i];  // r ranks the pair (jj < kk) among the m sites after i
+    const float b2m = (float)(2 * m - 1);
+    int jj = (int)((b2m - sqrtf(fmaxf(b2m * b2m - 8.f * (float)r, 0.f))) * 0.5f);
+    jj = max(0, min(jj, m - 2));
+    while ((jj + 1) * m - (jj + 1) * (jj + 2) / 2 <= r) ++jj;
+    while (jj * m - jj * (jj + 1) / 2 > r) --jj;
+    const int kk = r - (jj * m - jj * (jj + 1) / 2) + jj + 1;
+    const int j = i + 1 + jj, k = i + 1 + kk;
+    const double ax = sx[i], ay = sy[i], bx = sx[j], by = sy[j], cx = sx[k], cy = sy[k];
+    const double e1x = dsub(bx, ax), e1y = dsub(by, ay), e2x = dsub(cx, ax), e2y = dsub(cy, ay);
+    const double orient = dsub(dmul(e1x, e2y), dmul(e1y, e2x));
+    const double span = fmax(fmax(fabs(e1x), fabs(e1y)), fmax(fabs(e2x), fabs(e2y)));
+    bool alive = fabs(orient) > dmul(1e-12, fmax(dmul(span, span), 1e-300));  // not collinear / repeated sites
+    const double sgn = orient > 0.0 ? 1.0 : -1.0;
+    const float fax = fx[i], fay = fy[i], fbx = fx[j], fby = fy[j], fcx = fx[k], fcy = fy[k], fsgn = (float)sgn;
+#pragma unroll 1
+    for (int q = 0; q < 12 && alive; ++q) {
+      const int off = 1 + q / 6, r6 = q - (q / 6) * 6;
+      const int base = r6 < 2 ? i : (r6 < 4 ? j : k);
+      int d = base + ((r6 & 1) ? -off : off);
+      d = d < 0 ? d + NS : (d >= NS ? d - NS : d);
+      if (d == i || d == j || d == k) continue;
+      const int screen = incircle_screen(fax, fay, fbx, fby, fcx, fcy, fx[d], fy[d], fsgn);
+      if (screen > 0 || (screen == 0 && incircle_exact(ax, ay, bx, by, cx, cy, sx[d], sy[d], sgn))) alive = false;
+    }
+    if (alive) queue[atomicAdd(&n_queue, 1)] = TriRec{i, j, k, sgn > 0.0 ? 1 : -1};
   }
-  const int i = lo, m = NS - 1 - i, r = t - before[i];  // r ranks the pair (jj < kk) among the m sites after i
-  const float b2m = (float)(2 * m - 1);
-  int jj = (int)((b2m - sqrtf(fmaxf(b2m * b2m - 8.f * (float)r, 0.f))) * 0.5f);
-  jj = max(0, min(jj, m - 2));
-  while ((jj + 1) * m - (jj + 1) * (jj + 2) / 2 <= r) ++jj;
-  while (jj * m - jj * (jj + 1) / 2 > r) --jj;
-  const int kk = r - (jj * m - jj * (jj + 1) / 2) + jj + 1;
-  const int j = i + 1 + jj, k = i + 1 + kk;
-  const double ax = sx[i], ay = sy[i], bx = sx[j], by = sy[j], cx = sx[k], cy = sy[k];
-  const double e1x = dsub(bx, ax), e1y = dsub(by, ay), e2x = dsub(cx, ax), e2y = dsub(cy, ay);
-  const double orient = dsub(dmul(e1x, e2y), dmul(e1y, e2x));
-  const double span = fmax(fmax(fabs(e1x), fabs(e1y)), fmax(fabs(e2x), fabs(e2y)));
-  if (!(fabs(orient) > dmul(1e-12, fmax(dmul(span, span), 1e-300)))) return;  // collinear or repeated sites
-  const double sgn = orient > 0.0 ? 1.0 : -1.0;
-  const float fax = fx[i], fay = fy[i], fbx = fx[j], fby = fy[j], fcx = fx[k], fcy = fy[k], fsgn = (float)sgn;
-  int d = i;
-  for (int s = 0; s < NS - 1; ++s) {
-    d = (d + 1 == NS) ? 0 : d + 1;
-    if (d == j || d == k) continue;
-    const int screen = incircle_screen(fax, fay, fbx, fby, fcx, fcy, fx[d], fy[d], fsgn);
-    if (screen > 0) return;
-    if (screen < 0) continue;
-    const double px = sx[d], py = sy[d];
-    const double adx = dsub(ax, px), ady = dsub(ay, py);
-    const double bdx = dsub(bx, px), bdy = dsub(by, py);
-    const double cdx = dsub(cx, px), cdy = dsub(cy, py);
-    const double a2 = dadd(dmul(adx, adx), dmul(ady, ady));
-    const double b2 = dadd(dmul(bdx, bdx), dmul(bdy, bdy));
-    const double c2 = dadd(dmul(cdx, cdx), dmul(cdy, cdy));
-    const double t1 = dmul(adx, dsub(dmul(bdy, c2), dmul(b2, cdy)));
-    const double t2 = dmul(ady, dsub(dmul(bdx, c2), dmul(b2, cdx)));
-    const double t3 = dmul(a2, dsub(dmul(bdx, cdy), dmul(bdy, cdx)));
-    const double det = dmul(dadd(dsub(t1, t2), t3), sgn);  // > 0: site d strictly inside the circumcircle
-    const double mag = dadd(dadd(fabs(t1), fabs(t2)), fabs(t3));
-    if (det > dmul(INCIRCLE_TOL, mag)) return;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, nq = n_queue;
+  for (int s = threadIdx.x >> 5; s < nq; s += 4) {
+    const TriRec tr = queue[s];
+    const double sgn = (double)tr.key;
+    bool inside = false;
+    for (int d = lane; d < NS && !inside; d += 32) {
+      if (d == tr.i || d == tr.j || d == tr.k) continue;
+      const int screen = incircle_screen(fx[tr.i], fy[tr.i], fx[tr.j], fy[tr.j], fx[tr.k], fy[tr.k], fx[d], fy[d], (float)tr.key);
+      inside = screen > 0 || (screen == 0 && incircle_exact(sx[tr.i], sy[tr.i], sx[tr.j], sy[tr.j], sx[tr.k], sy[tr.k],
+                                                             sx[d], sy[d], sgn));
+    }
+    if (!__any_sync(0xffffffffu, inside) && lane == 0) {
+      const int slot = atomicAdd(&counts[f], 1);
+      if (slot < MAXT) tris[(size_t)f * MAXT + slot] = TriRec{tr.i, tr.j, tr.k, (tr.i * NS + tr.j) * NS + tr.k};
+    }
   }
-  const int slot = atomicAdd(&counts[f], 1);
-  if (slot < MAXT) tris[(size_t)f * MAXT + slot] = TriRec{i, j, k, (i * NS + j) * NS + k};
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -145,8 +174,18 @@ __global__ void __launch_bounds__(128) delaunay_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------------------------
 struct TileTri {
   double r2x, r2y, m00, m01, m10, m11, det;
+  double lim;  // -1e-6 * det^2: "barycentric coordinate >= -1e-6" without the division (numerator * det >= lim)
   int i, j, k, key;
 };
+
+// Division-free screen: the three barycentric numerators times det.  c_e >= -1e-6 <=> n_e * det >= -1e-6 * det^2.  A
+// strict superset of the exact test below (tolerance 1e-9, rounding ~1e-13), at a seventh of its cost: the two fp64
+// divisions of the exact formula are only paid for the one or two triangles that really contain the pixel.
+__device__ __forceinline__ void bary_numerators(const TileTri& t, double qx, double qy, double& n0, double& n1, double& n2) {
+  const double dx = qx - t.r2x, dy = qy - t.r2y;
+  const double a0 = t.m11 * dx - t.m01 * dy, a1 = t.m00 * dy - t.m10 * dx;
+  n0 = a0 * t.det; n1 = a1 * t.det; n2 = (t.det - a0 - a1) * t.det;
+}
 
 __device__ __forceinline__ void bary(const TileTri& t, double qx, double qy, double& c0, double& c1, double& c2) {
   const double dx = dsub(qx, t.r2x), dy = dsub(qy, t.r2y);
@@ -176,16 +215,17 @@ __global__ void __launch_bounds__(256) motion_raster_kernel(const float* __restr
     tt.m00 = dsub(dsx[r.i], tt.r2x); tt.m01 = dsub(dsx[r.j], tt.r2x);
     tt.m10 = dsub(dsy[r.i], tt.r2y); tt.m11 = dsub(dsy[r.j], tt.r2y);
     tt.det = dsub(dmul(tt.m00, tt.m11), dmul(tt.m01, tt.m10));
+    tt.lim = -1e-6 * tt.det * tt.det;
     tt.i = r.i; tt.j = r.j; tt.k = r.k; tt.key = r.key;
     double mx0 = -1e300, mx1 = -1e300, mx2 = -1e300;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      double c0, c1, c2;
-      bary(tt, (double)(x0 + (c & 1) * 31), (double)(y0 + (c >> 1) * 7), c0, c1, c2);
-      mx0 = fmax(mx0, c0); mx1 = fmax(mx1, c1); mx2 = fmax(mx2, c2);
+      double n0, n1, n2;
+      bary_numerators(tt, (double)(x0 + (c & 1) * 31), (double)(y0 + (c >> 1) * 7), n0, n1, n2);
+      mx0 = fmax(mx0, n0); mx1 = fmax(mx1, n1); mx2 = fmax(mx2, n2);
     }
     // 1e-6 of slack on the cull: it only has to be conservative, the per-pixel test below decides
-    if (mx0 >= -1e-6 && mx1 >= -1e-6 && mx2 >= -1e-6) list[atomicAdd(&n_list, 1)] = tt;
+    if (mx0 >= tt.lim && mx1 >= tt.lim && mx2 >= tt.lim) list[atomicAdd(&n_list, 1)] = tt;
   }
   __syncthreads();
   const int n = n_list;
@@ -195,6 +235,9 @@ __global__ void __launch_bounds__(256) motion_raster_kernel(const float* __restr
   double b0 = 0.0, b1 = 0.0, b2 = 0.0;
   for (int t = 0; t < n; ++t) {
     double c0, c1, c2;
+    bary_numerators(list[t], qx, qy, c0, c1, c2);
+    const double lim = list[t].lim;
+    if (!(c0 >= lim && c1 >= lim && c2 >= lim) || list[t].key >= best_key) continue;
     bary(list[t], qx, qy, c0, c1, c2);
     if (c0 >= -INSIDE_TOL && c1 >= -INSIDE_TOL && c2 >= -INSIDE_TOL && list[t].key < best_key) {
       best = t; best_key = list[t].key; b0 = c0; b1 = c1; b2 = c2;
