@@ -35,6 +35,29 @@ UNIT = "frames/s"
 N_INPUT_SETS = 4  # 4 x 42 MB of distinct inputs > 126 MB L2; the per-step working set (GBs) flushes L2 anyway
 
 
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner comes from NCCL_DEBUG in
+    the environment or in /etc/nccl.conf), so file descriptor 1 is pointed at stderr for the whole run and the JSON line
+    goes to the saved descriptor."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -131,7 +154,7 @@ def run_reference(args, rank):
                              "sample": f"{args.steps} steps x {Bs} frames, torch {torch.__version__} CPU, all host threads"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 CLIP_METRIC_NOTE = ("configs[2]: one photo + {T} target landmark sets (12 s clip), landmark maps + Delaunay motion field on the "
@@ -202,7 +225,7 @@ def run_reference_clip(args, rank):
                        + f"; step = {n}-frame sample of the clip"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_clip(args, rank, local_rank, world):
@@ -368,7 +391,7 @@ def run_clip(args, rank, local_rank, world):
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "model_tflops": value * flops_frame / 1e12,
                 "tensor_frac_of_sustained_bf16": value / world * flops_frame / 1e12 / peaks["bf16_tflops_sustained"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -400,6 +423,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    claim_stdout()
 
     if args.impl == "reference":
         (run_reference_clip if clip else run_reference)(args, rank)
@@ -572,7 +596,7 @@ def main():
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "model_tflops": value * flops_frame / 1e12,
                 "tensor_frac_of_sustained_bf16": value / world * flops_frame / 1e12 / peaks["bf16_tflops_sustained"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
