@@ -5,9 +5,9 @@ re-cut so that what does not depend on the frame is done once and what does is b
 Per clip (hoisted):
   * the photo matting  real_A = ((real_A/2+.5)*mask + 1-mask)*2-1   (geomcgt_ifw_test_model.py:280,292)
   * the source landmark map  A_lm = draw2(A_lm_68)                  (umlvdfw_test_dataset.py:147)
-  * inside netG, everything that depends on the photo alone: the three 7x7 stems, model_tri11, model_tri21,
-    model_tri22 and their InstanceNorms (networks.py:1318-1328) run once per batch, not once per frame
-    (`ap_netg_forward_shared_photo`)
+  * inside netG, everything that depends on the photo and its landmark map alone: the three 7x7 stems, model_tri11,
+    model_tri21, model_tri22, model_landmark_trans(A_lm) and their InstanceNorms (networks.py:1318-1331) run once per
+    batch, not once per frame (`ap_netg_forward_shared_photo`)
   * the static drawing fakeB_static and the matte are INPUTS here: the reference recomputes them with MODNet and the
     512x512 static generator for every frame of the same photo (geomcgt_ifw_test_model.py:279-291); both networks need
     checkpoints that do not ship and are outside the path this repo rebuilds.
@@ -111,7 +111,7 @@ class ClipRenderer:
             else:
                 ifm = if_mask[s:e]
             if self.share_photo:
-                fake = self.netG.forward_shared_photo(p["real_A"], land1, land2, motion, flow, ifm)
+                fake = self.netG.forward_shared_photo(p["real_A"], p["land1"], land2, motion, flow, ifm)
             else:
                 fake = self.netG(photo, land1, land2, motion, flow, ifm)
             if mask is not None:

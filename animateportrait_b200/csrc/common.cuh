@@ -131,6 +131,7 @@ struct ApplyP {
   FlagWait wait0, wait1;
   uint32_t* done_flags;
   int l2_hints;      // raw loads evict_first (set by launch_apply from AP_NETG_L2_HINTS bit 1)
+  int src_shared;    // 1: `raw`/`stats` hold ONE image that is normalised into every image of the destination (clip mode)
 };
 
 struct WarpP {
@@ -241,7 +242,7 @@ int launch_out_umma(const OutConvP& p, const uint8_t* wimg, cudaStream_t st);
 
 // ---- landmark branch (landmark.cu): three direct convs over both landmark maps ----
 int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
-                           const Raw& r0, const Raw& r1, const Raw& r2, int B, cudaStream_t st);
+                           const Raw& r0, const Raw& r1, const Raw& r2, int B1, int B2, cudaStream_t st);
 
 ConvTaps make_taps_conv(int k, int pad, int extra_origin);
 ConvTaps make_taps_convT_phase(int py, int px);

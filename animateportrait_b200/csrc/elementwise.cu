@@ -51,11 +51,12 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   const int HW = p.H * p.W;
   const int logW = 31 - __clz(p.W);
   float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int ns = p.src_shared ? 0 : n;  // clip mode: one source image for every destination image (MODE 0 only)
   auto finalise_stats = [&]() {
     const double inv_n = 1.0 / (double)HW;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
+      if (p.stats) stats_to_affine(p.stats, ns, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
       else { mean[e] = p.bias ? -p.bias[c + e] : 0.f; rstd[e] = 1.f; }
       if (MODE == 1) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
     }
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   if (UNROLL != 8) finalise_stats();
   Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
   const int pix0 = blockIdx.x * APPLY_PIX_PER_CTA + py;
-  const float* raw = p.raw + ((size_t)n * HW) * p.raw_C + p.raw_coff + c;
+  const float* raw = p.raw + ((size_t)ns * HW) * p.raw_C + p.raw_coff + c;
   const float* raw2 = (MODE == 1) ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
   const float* rin = (MODE == 2) ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
   float* rout = p.res_out ? p.res_out + ((size_t)n * HW) * p.C + c : nullptr;
@@ -223,6 +224,8 @@ int launch_apply(const ApplyP& p_in, cudaStream_t st) {
   AP_REQUIRE((p.raw2 != nullptr) + (p.res_in != nullptr) + (p.res_fmt >= 0) <= 1, AP_ERR_INVALID,
              "apply: shortcut operand and residual stream are exclusive");
   AP_REQUIRE(p.res_fmt < 0 || p.res_fmt == FMT_F32 || p.res_fmt == FMT_BF16X2, AP_ERR_INVALID, "apply: residual format");
+  AP_REQUIRE(!p.src_shared || (!p.raw2 && !p.res_in && p.res_fmt < 0 && !p.res_out), AP_ERR_INVALID,
+             "apply: a shared source image goes with the plain InstanceNorm mode only");
   const int ppc = 8 * (256 / (p.C / 4));  // pixels per CTA (matches APPLY_PIX_PER_CTA in the kernel)
   AP_REQUIRE((p.W & (p.W - 1)) == 0 && (p.H * p.W) % ppc == 0, AP_ERR_INVALID, "apply: %dx%d", p.H, p.W);
   dim3 grid(p.H * p.W / ppc, p.B);

@@ -20,12 +20,12 @@ bool carveout_enabled();
 // channel loops fully unrolled every FMA reads its weight straight from the constant bank, no load at all.
 template <int CIN, int COUT>
 struct LandP {
-  const float* in0;   // CIN == 1: land1 [B,1,256,256];  else raw NHWC [2B,Hin,Win,CIN]
-  const float* in1;   // CIN == 1: land2
-  const double* in_stats;  // [2B][CIN][2] (CIN > 1)
-  float* out;         // raw NHWC [2B,Hout,Wout,COUT]
-  double* out_stats;  // [2B][COUT][2]
-  int B, Hin, Hout;
+  const float* in0;   // CIN == 1: land1 [B1,1,256,256];  else raw NHWC [B1+B2,Hin,Win,CIN]
+  const float* in1;   // CIN == 1: land2 [B2,1,256,256]
+  const double* in_stats;  // [B1+B2][CIN][2] (CIN > 1)
+  float* out;         // raw NHWC [B1+B2,Hout,Wout,COUT]
+  double* out_stats;  // [B1+B2][COUT][2]
+  int B, Hin, Hout;   // B = B1, the number of land1 maps (the batch size, or 1 in clip mode: one source landmark map)
   float w[9 * CIN * COUT];
 };
 
@@ -112,11 +112,12 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
   }
 }
 
-// land1/land2 [B,1,256,256] -> raw [2B,64,64,16] + stats; r0/r1 are workspace raws (with stats).
+// land1 [B1,1,256,256], land2 [B2,1,256,256] -> raw [B1+B2,64,64,16] + stats; r0/r1 are workspace raws (with stats).
 // w0/w1/w2 are HOST arrays in [slab][Cin][Cout] order.
 int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
-                           const Raw& r0, const Raw& r1, const Raw& r2, int B, cudaStream_t st) {
-  AP_REQUIRE(r0.B == 2 * B && r1.B == 2 * B && r2.B == 2 * B, AP_ERR_INVALID, "landmark: workspace batch");
+                           const Raw& r0, const Raw& r1, const Raw& r2, int B1, int B2, cudaStream_t st) {
+  const int NB = B1 + B2;
+  AP_REQUIRE(r0.B == NB && r1.B == NB && r2.B == NB, AP_ERR_INVALID, "landmark: workspace batch");
   static bool once = false;
   if (!once && carveout_enabled()) {  // co-residency with the stem kernel's all-shared-memory SM configuration (see elementwise.cu)
     cudaFuncSetAttribute(land_conv_kernel<1, 8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -125,21 +126,21 @@ int launch_landmark_branch(const float* land1, const float* land2, const float* 
     once = true;
   }
   {
-    LandP<1, 8> a{land1, land2, nullptr, r0.p, r0.stats, B, 256, 256, {}};
+    LandP<1, 8> a{land1, land2, nullptr, r0.p, r0.stats, B1, 256, 256, {}};
     memcpy(a.w, w0, sizeof(a.w));
-    land_conv_kernel<1, 8, 1><<<2 * B * 65536 / 256, 256, 0, st>>>(a);
+    land_conv_kernel<1, 8, 1><<<NB * 65536 / 256, 256, 0, st>>>(a);
     AP_CUDA(cudaGetLastError());
   }
   {
-    LandP<8, 16> b{r0.p, nullptr, r0.stats, r1.p, r1.stats, B, 256, 128, {}};
+    LandP<8, 16> b{r0.p, nullptr, r0.stats, r1.p, r1.stats, B1, 256, 128, {}};
     memcpy(b.w, w1, sizeof(b.w));
-    land_conv_kernel<8, 16, 2><<<2 * B * 16384 / 256, 256, 0, st>>>(b);
+    land_conv_kernel<8, 16, 2><<<NB * 16384 / 256, 256, 0, st>>>(b);
     AP_CUDA(cudaGetLastError());
   }
   {
-    LandP<16, 16> c{r1.p, nullptr, r1.stats, r2.p, r2.stats, B, 128, 64, {}};
+    LandP<16, 16> c{r1.p, nullptr, r1.stats, r2.p, r2.stats, B1, 128, 64, {}};
     memcpy(c.w, w2, sizeof(c.w));
-    land_conv_kernel<16, 16, 2><<<2 * B * 4096 / 256, 256, 0, st>>>(c);
+    land_conv_kernel<16, 16, 2><<<NB * 4096 / 256, 256, 0, st>>>(c);
     AP_CUDA(cudaGetLastError());
   }
   launches_add(3);

@@ -394,6 +394,7 @@ struct Runner {
             FlagWait fl_w0 = FlagWait{nullptr, 0}, FlagWait fl_w1 = FlagWait{nullptr, 0}, uint32_t* fl_done = nullptr) {
     if (ph != PH_EXEC) return AP_OK;
     ApplyP p = make_apply(r, rcoff, C, relu, dst, dcoff, halo, bias, r2, res_in, res_out, res_act);
+    if (dst && r.B == 1 && dst->B > 1) { p.B = dst->B; p.src_shared = 1; }  // clip mode: one image into every frame's slot
     if (fl_done != nullptr || fl_w0.flags != nullptr) {
       p.wait0 = fl_w0; p.wait1 = fl_w1; p.done_flags = fl_done;
       AP_TRY(launch_apply_flags(p, st));
@@ -485,24 +486,25 @@ int Runner::run(const Inputs& in) {
 
   // ---- landmark branch on land1 and land2 as one batch of 2B maps (networks.py:1280-1282, 1331-1332) ----
   {
-    Raw rl0 = raw(2 * B, 256, 256, 8, true);
-    Raw rl1 = raw(2 * B, 128, 128, 16, true);
-    Raw rl2 = raw(2 * B, 64, 64, 16, true);
+    const int B1 = Bp;  // land1 is the SOURCE landmark map: it belongs to the photo (one map in clip mode)
+    Raw rl0 = raw(B1 + B, 256, 256, 8, true);
+    Raw rl1 = raw(B1 + B, 128, 128, 16, true);
+    Raw rl2 = raw(B1 + B, 64, 64, 16, true);
     AP_TRY(order_after(s3, main_st));
     on(s3);
     AP_TRY(wait_input(2));
     if (ph == PH_EXEC) {
       AP_TRY(launch_landmark_branch(in.land1, in.land2, W("model_landmark_trans.0").host.data(),
                                     W("model_landmark_trans.3").host.data(), W("model_landmark_trans.6").host.data(), rl0,
-                                    rl1, rl2, B, st));
-      AP_TRY(mark(CL_LAND, 2.0 * 2 * B * 9.0 * (65536.0 * 8 + 16384.0 * 8 * 16 + 4096.0 * 16 * 16)));
+                                    rl1, rl2, B1, B, st));
+      AP_TRY(mark(CL_LAND, 2.0 * (B1 + B) * 9.0 * (65536.0 * 8 + 16384.0 * 8 * 16 + 4096.0 * 16 * 16)));
     }
     for (int li = 0; li < 2; ++li) {
-      Raw v = rl2;  // view of this landmark's half of the batch
-      v.B = B;
+      Raw v = rl2;  // view of this landmark's part of the batch: [0, B1) = land1, [B1, B1 + B) = land2
+      v.B = li == 0 ? B1 : B;
       if (ph != PH_SIZE) {
-        v.p = rl2.p + (size_t)li * B * 64 * 64 * 16;
-        v.stats = rl2.stats + (size_t)li * B * 16 * 2;
+        v.p = rl2.p + (size_t)li * B1 * 64 * 64 * 16;
+        v.stats = rl2.stats + (size_t)li * B1 * 16 * 2;
       }
       for (int k = 0; k < (res_from_act ? 9 : 3); k += 3) AP_TRY(apply(v, 0, 16, 0, &Xb[k], 256 + 16 * li, 1));
       tap_act(li == 0 ? "land1" : "land2", Xb[0], 256 + 16 * li, 16);

@@ -188,14 +188,14 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
 
     @torch.no_grad()
     def forward_shared_photo(self, input, land1, land2, motion, flow, ifmask):
-        """Clip form of forward(): `input` is ONE photo [1,3,256,256] shared by the B frames the other five tensors
-        describe (`ap_netg_forward_shared_photo`): the photo-only part of the encoder runs once per call.  Same result as
-        forward(input.expand(B, ...), ...)."""
+        """Clip form of forward(): `input` is ONE photo [1,3,256,256] and `land1` its landmark map [1,1,256,256], shared
+        by the B frames the other four tensors describe (`ap_netg_forward_shared_photo`): the layers that depend on
+        them alone run once per call.  Same result as forward(input.expand(B, ...), land1.expand(B, ...), ...)."""
         if not input.is_cuda:
             raise RuntimeError("the B200 generator runs on CUDA tensors only (no CPU fallback)")
         dev = input.device
         B = land2.shape[0]
-        want = {"input": (1, 3, 256, 256), "land1": (B, 1, 256, 256), "land2": (B, 1, 256, 256),
+        want = {"input": (1, 3, 256, 256), "land1": (1, 1, 256, 256), "land2": (B, 1, 256, 256),
                 "motion": (B, 256, 256, 2), "flow": (B, 2, 256, 256), "ifmask": (B, 1, 256, 256)}
         ts = []
         for (name, shape), t in zip(want.items(), (input, land1, land2, motion, flow, ifmask)):

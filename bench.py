@@ -340,7 +340,7 @@ def run_clip(args, rank, local_rank, world):
             if args.no_share_photo:
                 net(photo_b, land1_b, land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
             else:
-                net.forward_shared_photo(photo_b[:1], land1_b, land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
+                net.forward_shared_photo(photo_b[:1], land1_b[:1], land2_b, motion_b, flow_d[:nb], ifm_d[:nb])
             p = net.get_profile()
             if prof is None:
                 prof = p

@@ -70,9 +70,10 @@ int ap_netg_forward(ap_netg* handle, int B, const float* input, const float* lan
 
 /* Clip form of the same call: ONE photo shared by all B frames of the batch (the reference renders a clip frame by
  * frame from the same photo, Module2/test.py:58-65, and recomputes the photo's features every time).
- * `input` is [1,3,256,256]; everything else as ap_netg_forward.  The part of the encoder that depends on the photo
- * alone (model_tri00/10/20 stems, model_tri11, model_tri21, model_tri22; networks.py:1318-1328) runs once per call and
- * the three double warps read it for every frame.  Same results as ap_netg_forward on B copies of the photo. */
+ * `input` is [1,3,256,256] and `land1` (the SOURCE landmark map, which belongs to the photo) [1,1,256,256]; everything
+ * else as ap_netg_forward.  The part of the network that depends on them alone (model_tri00/10/20 stems, model_tri11,
+ * model_tri21, model_tri22, model_landmark_trans(land1); networks.py:1318-1331) runs once per call; the three double
+ * warps and the ResnetBlock2 inputs read it for every frame.  Same results as ap_netg_forward on B copies of both. */
 int ap_netg_forward_shared_photo(ap_netg* handle, int B, const float* input, const float* land1, const float* land2,
                                  const float* motion, const float* flow, const float* ifmask, float* out,
                                  void* cuda_stream);

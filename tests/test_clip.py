@@ -140,15 +140,17 @@ def test_shared_photo_forward_equals_forward_on_copies_of_the_photo(precision):
     x, l1, l2, motion, flow, ifm = (t.to(dev) for t in synth.make_inputs(B, seed=77, kind="smooth"))
     photo = x[:1].contiguous()
     with torch.no_grad():
+        l1 = l1[:1].expand(B, 1, 256, 256).contiguous()          # one source landmark map, as in a clip
         want = net(photo.expand(B, 3, 256, 256).contiguous(), l1, l2, motion, flow, ifm)
-        got = net.forward_shared_photo(photo, l1, l2, motion, flow, ifm)
+        got = net.forward_shared_photo(photo, l1[:1], l2, motion, flow, ifm)
         assert got.shape == want.shape
         assert (got - want).abs().max().item() <= (0.1 if precision == "bf16" else 2e-4)
         for tap in ("tri00", "tri11", "tri22"):                     # photo-only taps are a batch of one in clip mode
             assert net.debug_read(tap).shape[0] == 1
         assert net.debug_read("warp2").shape[0] == B
         # B = 1 and a second batch size reuse nothing stale
+        assert (net.debug_read("land1") - net.debug_read("land1")[:1]).abs().max().item() == 0   # broadcast to all frames
         one = net.forward_shared_photo(photo, l1[:1], l2[:1], motion[:1], flow[:1], ifm[:1])
         assert (one - want[:1]).abs().max().item() <= (0.1 if precision == "bf16" else 2e-4)
     with pytest.raises(RuntimeError, match="input"):
-        net.forward_shared_photo(x, l1, l2, motion, flow, ifm)
+        net.forward_shared_photo(x, l1[:1], l2, motion, flow, ifm)

@@ -81,6 +81,17 @@ def test_oracle_triangulation_properties():
     assert abs(area.sum() - 255.0 * 255.0) < 1e-6     # the triangles tile the image square exactly once
 
 
+def test_oracle_triangulation_is_qhulls_on_sites_in_general_position():
+    spatial = pytest.importorskip("scipy.spatial")
+    rng = np.random.RandomState(17)
+    for trial in range(6):
+        lm = rng.uniform(-10 if trial % 2 else 5, 265 if trial % 2 else 250, (68, 2)).astype(np.float32)
+        sites, _ = O.motion_sites(lm, lm)
+        mine = {tuple(sorted(t)) for t in O.delaunay_triangles(sites).tolist()}
+        qhull = {tuple(sorted(t)) for t in spatial.Delaunay(sites).simplices.tolist()}
+        assert mine == qhull
+
+
 def test_oracle_motion_identity_and_affine_reproduction_under_cocircular_sites():
     # landmarks on an integer lattice: many co-circular quadruples, the Delaunay triangulation is not unique; every
     # valid choice still reproduces an affine map exactly (source = A * destination + b at all sites incl. the corners)

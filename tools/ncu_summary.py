@@ -15,7 +15,9 @@ WANT = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rdMB"), ("dr
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
         ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
         ("sm__cycles_active.avg", "cyc_act"), ("sm__cycles_elapsed.avg", "cyc"),
-        ("smsp__inst_executed.sum", "inst")]
+        ("smsp__inst_executed.sum", "inst"),
+        ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64%"),
+        ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes")]
 
 
 def to_unit(val, unit, want):
