@@ -144,13 +144,19 @@ def test_shared_photo_forward_equals_forward_on_copies_of_the_photo(precision):
         want = net(photo.expand(B, 3, 256, 256).contiguous(), l1, l2, motion, flow, ifm)
         got = net.forward_shared_photo(photo, l1[:1], l2, motion, flow, ifm)
         assert got.shape == want.shape
-        assert (got - want).abs().max().item() <= (0.1 if precision == "bf16" else 2e-4)
+        # bf16 mode: a last-bit change of a statistic flips bf16 roundings downstream; two valid bf16 evaluations differ by
+        # up to the mode's own error against the oracle (gate 0.1 / mean 0.012, measured 0.047 here), so bound the maximum
+        # loosely and the mean as well -- a mis-routed image would be O(1) everywhere
+        tol = 0.25 if precision == "bf16" else 2e-4
+        assert (got - want).abs().max().item() <= tol
+        if precision == "bf16":
+            assert (got - want).abs().mean().item() <= 0.03
         for tap in ("tri00", "tri11", "tri22"):                     # photo-only taps are a batch of one in clip mode
             assert net.debug_read(tap).shape[0] == 1
         assert net.debug_read("warp2").shape[0] == B
         # B = 1 and a second batch size reuse nothing stale
         assert (net.debug_read("land1") - net.debug_read("land1")[:1]).abs().max().item() == 0   # broadcast to all frames
         one = net.forward_shared_photo(photo, l1[:1], l2[:1], motion[:1], flow[:1], ifm[:1])
-        assert (one - want[:1]).abs().max().item() <= (0.1 if precision == "bf16" else 2e-4)
+        assert (one - want[:1]).abs().max().item() <= tol
     with pytest.raises(RuntimeError, match="input"):
         net.forward_shared_photo(x, l1[:1], l2, motion, flow, ifm)
