@@ -1,5 +1,4 @@
-// Device-side pieces of the InstanceNorm apply pass shared by elementwise.cu (stand-alone kernels) and conv_umma.cu
-// (apply warps fused into the trunk conv kernel).
+// Destination writer of the InstanceNorm apply pass and the double warp (elementwise.cu).
 #pragma once
 #include "common.cuh"
 
@@ -49,89 +48,6 @@ __device__ __forceinline__ void store_pixel(const Dst& d, int n, int y, int x, i
     if (ry >= 0) store4(d, (base + ry) * Wp + x + 1, c, v);
     if (rx >= 0) store4(d, (base + y + 1) * Wp + rx, c, v);
     if (ry >= 0 && rx >= 0) store4(d, (base + ry) * Wp + rx, c, v);
-  }
-}
-
-__device__ __forceinline__ float4 ld_coherent(const float* p) {
-  float4 r;
-  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
-  return r;
-}
-
-constexpr int AF_THREADS = 256, AF_TPP = 64, AF_NY = AF_THREADS / AF_TPP, AF_PIX = 8 * AF_NY;
-
-// `tid` in [0, AF_THREADS): the 256 threads that run this role (a whole CTA of apply_flags_kernel, or the apply warps
-// of a conv CTA); items first_item, first_item + item_stride, ... ; named barrier 2 synchronises exactly these threads.
-// UNROLL = pixel passes whose loads are in flight together (4 or 8; 8 for the fused role, whose 8 warps per SM must
-// sustain the whole HBM stream).
-template <int MODE, int UNROLL = 4>
-__device__ __forceinline__ void apply_flag_items(const ApplyP& p, int tid, int first_item, int item_stride) {
-  const int cq = tid % AF_TPP, py = tid / AF_TPP;
-  const int c = cq * 4;
-  const int HW = p.H * p.W;
-  const int logW = 31 - __clz(p.W);
-  const int items_per_img = HW / AF_PIX;
-  const int total = items_per_img * p.B;
-  Dst d{p.fmt, p.d0, p.d1, p.dC, p.dcoff, p.dpad, p.H, p.W, p.halo_reflect};
-  float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur = -1;
-  for (int item = first_item; item < total; item += item_stride) {
-    const int n = item / items_per_img;
-    const int pix0 = (item - n * items_per_img) * AF_PIX + py;
-    if (n != cur) {
-      if (tid == 0) {
-        if (p.wait0.flags) flag_wait(p.wait0.flags + n, p.wait0.expected);
-        if (p.wait1.flags) flag_wait(p.wait1.flags + n, p.wait1.expected);
-      }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      const double inv_n = 1.0 / (double)HW;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (p.stats) stats_to_affine(p.stats, n, p.stat_C, p.stat_coff, c + e, inv_n, &mean[e], &rstd[e]);
-        else { mean[e] = p.bias ? -p.bias[c + e] : 0.f; rstd[e] = 1.f; }
-        if (MODE == 1) stats_to_affine(p.stats2, n, p.stat2_C, p.stat2_coff, c + e, inv_n, &mean2[e], &rstd2[e]);
-      }
-      cur = n;
-    }
-    const float* raw = p.raw + ((size_t)n * HW) * p.raw_C + p.raw_coff + c;
-    const float* raw2 = (MODE == 1) ? p.raw2 + ((size_t)n * HW) * p.raw2_C + p.raw2_coff + c : nullptr;
-    const float* rin = (MODE == 2) ? p.res_in + ((size_t)n * HW) * p.C + c : nullptr;
-    float* rout = p.res_out ? p.res_out + ((size_t)n * HW) * p.C + c : nullptr;
-#pragma unroll 1
-    for (int k0 = 0; k0 < AF_PIX; k0 += UNROLL * AF_NY) {
-      float4 v[UNROLL], u[UNROLL];
-#pragma unroll
-      for (int j = 0; j < UNROLL; ++j) {
-        const int pix = pix0 + k0 + j * AF_NY;
-        v[j] = ld_coherent(raw + (size_t)pix * p.raw_C);
-        if (MODE == 1) u[j] = ld_coherent(raw2 + (size_t)pix * p.raw2_C);
-        if (MODE == 2) u[j] = ld_coherent(rin + (size_t)pix * p.C);
-      }
-#pragma unroll
-      for (int j = 0; j < UNROLL; ++j) {
-        const int pix = pix0 + k0 + j * AF_NY;
-        float4 o;
-        o.x = (v[j].x - mean[0]) * rstd[0];
-        o.y = (v[j].y - mean[1]) * rstd[1];
-        o.z = (v[j].z - mean[2]) * rstd[2];
-        o.w = (v[j].w - mean[3]) * rstd[3];
-        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (MODE == 1) {
-          o.x += (u[j].x - mean2[0]) * rstd2[0];
-          o.y += (u[j].y - mean2[1]) * rstd2[1];
-          o.z += (u[j].z - mean2[2]) * rstd2[2];
-          o.w += (u[j].w - mean2[3]) * rstd2[3];
-        }
-        if (MODE == 2) { o.x += u[j].x; o.y += u[j].y; o.z += u[j].z; o.w += u[j].w; }
-        if (rout) *reinterpret_cast<float4*>(rout + (size_t)pix * p.C) = o;
-        if (p.fmt >= 0) store_pixel(d, n, pix >> logW, pix & (p.W - 1), c, o);
-      }
-    }
-    if (p.done_flags) {
-      __threadfence();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (tid == 0) flag_add(p.done_flags + n, 1u);
-    }
   }
 }
 

@@ -35,15 +35,6 @@ void set_error(const char* fmt, ...);
     }                               \
   } while (0)
 
-// Device-side per-image dependency flags ("flag sync") for the conv -> InstanceNorm apply -> conv chain of the trunk.
-// A producer kernel adds to done[img] as its work on image img lands in memory; the consumer spins (acquire) until the
-// count reaches `expected` before touching that image.  The apply pass then runs on a side stream UNDER the conv that
-// feeds it, image by image, instead of after it (InstanceNorm needs whole planes, not whole batches).
-struct FlagWait {
-  const uint32_t* flags;  // [B], or null
-  uint32_t expected;
-};
-
 // Activation formats in HBM. All activations are NHWC; `pad` is a halo of that many pixels on each
 // side of H and W that the PRODUCER fills (reflection) or leaves zero.
 enum ActFmt : int {
@@ -62,11 +53,43 @@ struct Act {
   size_t elems() const { return pixels() * C; }
 };
 
+// InstanceNorm statistics of a producer kernel, deterministic and independent of the batch size: every producer warp
+// (or CTA) stores the {sum, sum of squares} of ITS pixels of an image as one partial row -- no two producers share an
+// address, nothing is accumulated with atomics -- and takes a ticket per (image, 32-channel block); whoever draws the
+// last ticket adds the `np` rows of the block up in row order (fp64) and writes the final [B][C][2] doubles.  Which
+// pixels a row covers depends on the image geometry only, never on the batch size, the grid or the timing, so the
+// statistics are bit-identical from run to run and between a batch and its frames run one by one -- like the
+// reference's CPU instance_norm (Module2/models/networks.py:34).  The ticket counters return to zero by themselves.
+struct StatSink {
+  double* stats;    // [B][C][2] final {sum, sumsq}; null: no statistics
+  float2* part;     // [B][np][C] partial rows
+  uint32_t* count;  // [B][C/32] tickets
+  int C, coff;      // channels of the statistics tensor, first channel this producer writes (multiple of 32)
+  int np;           // partial rows per image that make a complete plane
+};
+
 // Raw (pre-InstanceNorm) conv output: fp32 NHWC, no halo, plus per-(n,c) {sum, sumsq} in double.
 struct Raw {
   int B = 0, H = 0, W = 0, C = 0;
   float* p = nullptr;
-  double* stats = nullptr;  // [B][C][2], zeroed at the start of every forward
+  double* stats = nullptr;     // [B][C][2]
+  float2* part = nullptr;      // [B][H*W/32][C] partial rows (upper bound of every producer's np)
+  uint32_t* count = nullptr;   // [B][ceil(C/32)]
+  StatSink sink(int np, int coff = 0) const { return StatSink{stats, part, count, C, coff, np}; }
+};
+
+// Pointers of the tensors a caller hands to one forward.  Kernels that touch caller memory read them from this table
+// in device memory (one per plan, refreshed by a one-thread kernel before every forward) instead of taking them as
+// launch parameters: the launch sequence of a plan is then identical from call to call and can be replayed as a CUDA
+// graph whatever buffers the caller passes.
+struct IoPtrs {
+  const float* input;
+  const float* land1;
+  const float* land2;
+  const float* motion;
+  const float* flow;
+  const float* ifmask;
+  float* out;
 };
 
 constexpr int AP_MAX_TAPS = 49;
@@ -127,9 +150,6 @@ struct ApplyP {
   // destination (may be absent: fmt = -1)
   int fmt; void* d0; void* d1; int dC, dcoff, dpad;
   int halo_reflect;  // fill the halo ring by reflection (pad==1)
-  // flag sync (trunk only; C = 256): wait for up to two producers per image, signal own completion per image
-  FlagWait wait0, wait1;
-  uint32_t* done_flags;
   int l2_hints;      // raw loads evict_first (set by launch_apply from AP_NETG_L2_HINTS bit 1)
   int src_shared;    // 1: `raw`/`stats` hold ONE image that is normalised into every image of the destination (clip mode)
 };
@@ -137,9 +157,7 @@ struct ApplyP {
 struct WarpP {
   const float* raw; int raw_C, raw_coff;       // raw stem/conv output, normalised + ReLU on the fly
   const double* stats; int stat_C, stat_coff;
-  const float* motion;  // [B,256,256,2]
-  const float* flow;    // [B,2,256,256]
-  const float* ifmask;  // [B,1,256,256]
+  const IoPtrs* io;     // motion [B,256,256,2], flow [B,2,256,256], ifmask [B,1,256,256] of the caller
   int B, S, C, level;   // feature size S, feature channels C, pyramid level 0/1/2
   int src_shared;       // 1: `raw`/`stats` hold ONE image that every frame of the batch warps (clip mode)
   int fmt; void* d0; void* d1; int dC, dcoff, dpad;  // output: 2C channels at dcoff
@@ -149,7 +167,7 @@ struct OutConvP {
   const float* raw; const double* stats;  // model3.3 raw output [B,256,256,64] + stats (IN+ReLU on the fly)
   const float* w;                         // [onc][49][64] fp32
   const float* bias;                      // [onc]
-  float* out;                             // NCHW [B,onc,256,256]
+  const IoPtrs* io;                       // io->out: NCHW [B,onc,256,256] of the caller
   int B, onc;
 };
 
@@ -176,26 +194,43 @@ __device__ __forceinline__ void stats_to_affine(const double* st, int n, int sta
 #endif
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t expected) {
-  uint32_t v, spins = 0;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    if (v >= expected) break;
-    __nanosleep(128);
-    if (++spins > (1u << 21)) __trap();  // ~0.3 s: a lost dependency must fail the launch, never hang the GPU
-  }
+// One warp; lane L holds {sum, sumsq} over the warp's pixels of channel c0 + L: store partial row `row` of image n.
+__device__ __forceinline__ void stat_put(const StatSink& s, int n, int row, int c0, int lane, float cs, float cq) {
+  s.part[((size_t)n * s.np + row) * s.C + s.coff + c0 + lane] = make_float2(cs, cq);
 }
-__device__ __forceinline__ void flag_add(uint32_t* flag, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+// One warp, after it has stored its rows of `nblk` consecutive 32-channel blocks starting at channel c0 of image n:
+// one ticket per block; the last arriver of a block reduces it in row order.
+__device__ __forceinline__ void stat_arrive(const StatSink& s, int n, int c0, int nblk, int lane) {
+  __threadfence();
+  __syncwarp();
+  uint32_t* cnt = s.count + (size_t)n * (s.C >> 5) + ((s.coff + c0) >> 5);
+  uint32_t t = 0;
+  if (lane < nblk) t = atomicAdd(cnt + lane, 1u);
+  uint32_t last = __ballot_sync(0xffffffffu, lane < nblk && t == (uint32_t)(s.np - 1));
+  while (last) {
+    const int b = __ffs(last) - 1;
+    last &= last - 1;
+    __threadfence();
+    const float2* src = s.part + (size_t)n * s.np * s.C + s.coff + c0 + 32 * b + lane;
+    double su = 0.0, sq = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < s.np; ++r) {
+      const float2 v = __ldcg(src + (size_t)r * s.C);
+      su += (double)v.x;
+      sq += (double)v.y;
+    }
+    double* dst = s.stats + ((size_t)n * s.C + s.coff + c0 + 32 * b + lane) * 2;
+    dst[0] = su;
+    dst[1] = sq;
+    if (lane == 0) cnt[b] = 0;  // the counters are back at zero when the kernel ends
+  }
 }
 #endif
 
 // ---- launchers (each returns AP_OK / error and counts one launch) ----
 int launch_conv_simt(const SimtConvP& p, cudaStream_t st);
 int launch_apply(const ApplyP& p, cudaStream_t st);
-int launch_apply_flags(const ApplyP& p, cudaStream_t st);  // persistent, per-image flag sync (C = 256)
-uint32_t apply_flags_done_per_image(int H, int W);
-int apply_flags_regs_per_cta();
+int launch_set_io(IoPtrs* dst, const IoPtrs& v, cudaStream_t st);  // refreshes a plan's pointer table (one thread)
 int launch_warp(const WarpP& p, cudaStream_t st);
 int launch_out_conv(const OutConvP& p, cudaStream_t st);
 int launch_read(const ReadP& p, cudaStream_t st);
@@ -214,18 +249,22 @@ int launch_nchw_to_act(const float* src, const Act& dst, cudaStream_t st);  // d
 
 // ---- tcgen05 conv ----
 struct UmmaConv;  // opaque launch record (tensor maps + params), see conv_umma.cu
+// `sink`: where the InstanceNorm statistics of the output go (sink.stats null: none).  Partial row of (tile t of the
+// image, epilogue warp q) = (4 t + q) * slot_mul + slot_add: a layer computed by several convs over the same virtual
+// grid (the phases of a transposed conv) gives each conv its own slot_add < slot_mul; sink.np must be
+// 4 * tiles per image * slot_mul.
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff,
                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int nprod,
-                     float* out_raw, int out_C, int out_coff, double* stats, int stat_C, int stat_coff,
-                     const PhasePack* pk = nullptr, FlagWait wait = FlagWait{nullptr, 0}, uint32_t* done_flags = nullptr,
-                     const ApplyP* fuse = nullptr);
-uint32_t umma_conv_done_per_image(const UmmaConv* c);
+                     float* out_raw, int out_C, int out_coff, const StatSink& sink, int slot_mul = 1, int slot_add = 0,
+                     const PhasePack* pk = nullptr);
+int umma_conv_stat_rows(const ConvGeom& g);  // 4 * tiles per image of this geometry
 bool umma_pairs_available();  // CTA-pair kernels enabled and launchable on this device
-int umma_pair_regs_per_cta(); // registers one CTA of the trunk pair kernel occupies  // what done_flags[img] reaches when image img is complete
 void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
-int umma_init();  // resolves cuTensorMapEncodeTiled, sets func attributes
+int umma_init();  // resolves cuTensorMapEncodeTiled, sets the kernel attributes on the current device
 int umma_num_sms();
+int stem_umma_init_device();  // per-device kernel attributes of conv_stem.cu / conv_out.cu (called by umma_init)
+int out_umma_init_device();
 int tmap_encode(CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                 const uint32_t* box, const uint32_t* estr);
 int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C, int os, int py, int px);
@@ -233,7 +272,8 @@ int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C
 // ---- tcgen05 fused 7x7 stems (conv_stem.cu) ----
 size_t stem_umma_weight_bytes();
 int launch_pack_stem_umma(const float* src, int cout_s, int coff, uint8_t* img, cudaStream_t st);
-int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* stats, int B, int nprod, cudaStream_t st);
+int launch_stem_umma(const IoPtrs* io, const uint8_t* wimg, const Raw& out, int B, int nprod, cudaStream_t st);
+constexpr int STEM_STAT_ROWS = 512;  // 128 groups of 4 tiles x 4 epilogue warps per image
 
 // ---- tcgen05 output stage (conv_out.cu): IN+ReLU -> RefPad3 -> Conv7x7 64->onc -> bias -> tanh ----
 size_t out_umma_weight_bytes(int onc);
@@ -241,7 +281,7 @@ int launch_pack_out_umma(const float* src, int onc, uint8_t* img, cudaStream_t s
 int launch_out_umma(const OutConvP& p, const uint8_t* wimg, cudaStream_t st);
 
 // ---- landmark branch (landmark.cu): three direct convs over both landmark maps ----
-int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
+int launch_landmark_branch(const IoPtrs* io, const float* w0, const float* w1, const float* w2,
                            const Raw& r0, const Raw& r1, const Raw& r2, int B1, int B2, cudaStream_t st);
 
 ConvTaps make_taps_conv(int k, int pad, int extra_origin);

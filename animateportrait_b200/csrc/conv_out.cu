@@ -43,7 +43,7 @@ struct OutUmmaP {
   const double* stats;    // [B][64][2]
   const uint8_t* wimg;    // onc x O_WIMG pre-swizzled weight images
   const float* bias;      // [onc]
-  float* out;             // [B,onc,256,256]
+  const IoPtrs* io;       // io->out: [B,onc,256,256] of the caller (may be peer memory: plain stores)
   int B, onc, items;      // items = B * 256 tiles * onc
 };
 
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
     // ===================== epilogue (warps 17..20) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int et = (q << 5) | lane;  // a stable 0..127 index (any bijection works for the shifted sums)
+    float* out_base = p.io->out;
     for (int it = 0; it < nitems; ++it) {
       const int item = i_begin + it;
       const int tile = item / p.onc, o = item - tile * p.onc;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(O_THREADS, 1) out_umma_kernel(const __grid_con
       asm volatile("bar.sync 2, 128;" ::: "memory");    // t complete
       // part 2: shifted 49-term sums, 2 output pixels per thread
       const float b = p.bias[o];
-      float* dst = p.out + ((size_t)(img * p.onc + o) * 256 + ty * OT) * 256 + tx * OT;
+      float* dst = out_base + ((size_t)(img * p.onc + o) * 256 + ty * OT) * 256 + tx * OT;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int oy = (et >> 4) + 8 * k, ox = et & 15;
@@ -284,16 +285,19 @@ int launch_pack_out_umma(const float* src, int onc, uint8_t* img, cudaStream_t s
 
 static int g_out_sms = 0;
 
+int out_umma_init_device() {
+  int dev = 0;
+  AP_CUDA(cudaGetDevice(&dev));
+  AP_CUDA(cudaDeviceGetAttribute(&g_out_sms, cudaDevAttrMultiProcessorCount, dev));
+  AP_CUDA(cudaFuncSetAttribute(out_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O_SMEM));
+  return AP_OK;
+}
+
 int launch_out_umma(const OutConvP& q, const uint8_t* wimg, cudaStream_t st) {
   AP_REQUIRE(q.onc >= 1 && q.onc <= O_MAX_ONC, AP_ERR_UNSUPPORTED, "out conv: output_nc=%d", q.onc);
-  if (g_out_sms == 0) {
-    int dev = 0;
-    AP_CUDA(cudaGetDevice(&dev));
-    AP_CUDA(cudaDeviceGetAttribute(&g_out_sms, cudaDevAttrMultiProcessorCount, dev));
-    AP_CUDA(cudaFuncSetAttribute(out_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O_SMEM));
-  }
+  AP_TRY(umma_init());
   OutUmmaP p{};
-  p.raw = q.raw; p.stats = q.stats; p.wimg = wimg; p.bias = q.bias; p.out = q.out;
+  p.raw = q.raw; p.stats = q.stats; p.wimg = wimg; p.bias = q.bias; p.io = q.io;
   p.B = q.B; p.onc = q.onc; p.items = q.B * 256 * q.onc;
   const int grid = p.items < g_out_sms ? p.items : g_out_sms;
   out_umma_kernel<<<grid, O_THREADS, O_SMEM, st>>>(p);

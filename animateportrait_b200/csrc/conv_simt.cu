@@ -261,11 +261,12 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const OutConvP p) {
       }
     }
   }
+  float* outp = p.io->out;
 #pragma unroll
   for (int o = 0; o < ONC; ++o)
 #pragma unroll
     for (int r = 0; r < OC_ROWS; ++r)
-      p.out[((size_t)(n * ONC + o) * S + y0 + tg * OC_ROWS + r) * S + x0 + tx] = tanhf(acc[o][r] + p.bias[o]);
+      outp[((size_t)(n * ONC + o) * S + y0 + tg * OC_ROWS + r) * S + x0 + tx] = tanhf(acc[o][r] + p.bias[o]);
 }
 
 int launch_out_conv(const OutConvP& p, cudaStream_t st) {

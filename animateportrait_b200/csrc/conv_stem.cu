@@ -19,7 +19,8 @@
 //
 // Warp roles (416 threads): warp 0 = TMEM allocator, weight loader, MMA issuer; warps 1-8 = A builders (two groups
 // splitting the K range); warps 9-12 = epilogue (tcgen05.ld -> raw fp32 NHWC store + per-channel sum / sum of squares for the
-// following InstanceNorm, accumulated in registers across the CTA's tiles of one image).
+// following InstanceNorm, accumulated in registers across a GROUP of 4 consecutive tiles = two full image rows; CTAs own
+// whole groups, so the partial rows are the same for any batch size -- then stored through StatSink, common.cuh).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -44,10 +45,10 @@ constexpr size_t ST_SMEM = 1024 + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4 + 
 
 struct StemP {
   CUtensorMap tmO;       // fp32 NHWC output [B,256,256,160], box {32 ch, 32 px, 1 row, 1 image}
-  const float* in;       // [B,3,256,256] NCHW fp32
+  const IoPtrs* io;      // io->input: [B,3,256,256] NCHW fp32 of the caller
   const uint8_t* wimg;   // ST_WBYTES: [plane][chunk][160 rows][64 k] bf16, 128B-swizzled smem image
   float* out;            // raw NHWC [B,256,256,160]
-  double* stats;         // [B][160][2]
+  StatSink sink;         // [B][160][2]; partial row = 4 * (group of the image) + epilogue warp, np = STEM_STAT_ROWS
   int tiles;             // B * 512 (tile = 2 rows x 64 px)
   int dbg;               // AP_STEM_DBG timing probe: 1 = no output stores, 2 = no statistics, 4 = builders skip the A build
 };
@@ -104,10 +105,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sgen + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4 + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous tile range of this CTA
+  // contiguous range of tile groups of this CTA (4 tiles per group, 128 groups per image)
   const int G = gridDim.x;
-  const int t_begin = (int)(((long long)blockIdx.x * p.tiles) / G);
-  const int t_end = (int)(((long long)(blockIdx.x + 1) * p.tiles) / G);
+  const int ngroups = p.tiles >> 2;
+  const int t_begin = 4 * (int)(((long long)blockIdx.x * ngroups) / G);
+  const int t_end = 4 * (int)(((long long)(blockIdx.x + 1) * ngroups) / G);
   const int ntiles = t_end - t_begin;
 
   if (warp == 0) {
@@ -195,10 +197,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
       pch[k] = (idx < ST_PATCH) ? ((ch << 16) | (py << 8) | px) : -1;
     }
     float pre[NPRE];
+    const float* in_base = p.io->input;
     auto prefetch = [&](int t) {
       const int img = t >> 9, rem = t & 511;
       const int y0 = (rem >> 2) * 2, x0 = (rem & 3) * 64;
-      const float* src = p.in + (size_t)img * 3 * 65536;
+      const float* src = in_base + (size_t)img * 3 * 65536;
 #pragma unroll
       for (int k = 0; k < NPRE; ++k) {
         pre[k] = 0.f;
@@ -277,16 +280,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 64 + 8 * acc);
-      const bool flush = (it == ntiles - 1) || (((t + 1) >> 9) != img);
-      if (flush) {
+      if ((t & 3) == 3 && !(p.dbg & 2)) {  // end of a group of 4 tiles
+        const int row = ((rem >> 2) * 4 + q);
 #pragma unroll
         for (int g = 0; g < 5; ++g) {
-          double* st = p.stats + ((size_t)img * ST_N + g * 32 + lane) * 2;
-          atomicAdd(st, (double)ssum[g]);
-          atomicAdd(st + 1, (double)ssq[g]);
+          stat_put(p.sink, img, row, g * 32, lane, ssum[g], ssq[g]);
           ssum[g] = 0.f;
           ssq[g] = 0.f;
         }
+        stat_arrive(p.sink, img, 0, 5, lane);
       }
     }
     if (lane == 0) bulk_wait<0>();
@@ -332,23 +334,27 @@ size_t stem_umma_weight_bytes() { return ST_WBYTES; }
 
 static int g_stem_sms = 0;
 
-int launch_stem_umma(const float* in, const uint8_t* wimg, float* out, double* stats, int B, int nprod, cudaStream_t st) {
-  if (g_stem_sms == 0) {
-    int dev = 0;
-    AP_CUDA(cudaGetDevice(&dev));
-    AP_CUDA(cudaDeviceGetAttribute(&g_stem_sms, cudaDevAttrMultiProcessorCount, dev));
-    AP_CUDA(cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-    AP_CUDA(cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-  }
+int stem_umma_init_device() {
+  int dev = 0;
+  AP_CUDA(cudaGetDevice(&dev));
+  AP_CUDA(cudaDeviceGetAttribute(&g_stem_sms, cudaDevAttrMultiProcessorCount, dev));
+  AP_CUDA(cudaFuncSetAttribute(stem_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+  AP_CUDA(cudaFuncSetAttribute(stem_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+  return AP_OK;
+}
+
+int launch_stem_umma(const IoPtrs* io, const uint8_t* wimg, const Raw& out, int B, int nprod, cudaStream_t st) {
+  AP_TRY(umma_init());
   StemP p{};
-  AP_TRY(tmap_encode_out(&p.tmO, out, B, 256, 256, ST_N, 1, 0, 0));
-  p.in = in; p.wimg = wimg; p.out = out; p.stats = stats; p.tiles = B * 512;
+  AP_TRY(tmap_encode_out(&p.tmO, out.p, B, 256, 256, ST_N, 1, 0, 0));
+  p.io = io; p.wimg = wimg; p.out = out.p; p.sink = out.sink(STEM_STAT_ROWS); p.tiles = B * 512;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("AP_STEM_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
   }
-  const int grid = p.tiles < g_stem_sms ? p.tiles : g_stem_sms;
+  const int groups = p.tiles / 4;
+  const int grid = groups < g_stem_sms ? groups : g_stem_sms;
   if (nprod == 3)
     stem_umma_kernel<3><<<grid, ST_THREADS, ST_SMEM, st>>>(p);
   else

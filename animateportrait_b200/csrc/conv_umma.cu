@@ -19,14 +19,16 @@
 // * Two 256-column TMEM accumulators: the epilogue of item i overlaps the MMAs of item i+1.
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 //   warps 2..5 = epilogue: tcgen05.ld 32 columns at a time, stage them in a swizzled 4 KB slab and
-//   TMA-store the {32 ch, 32 px} box (coalesced, asynchronous), and reduce per-channel sum /
-//   sum-of-squares for the following InstanceNorm with a 31-shuffle butterfly per 32 columns.
+//   TMA-store the {32 ch, 32 px} box (coalesced, asynchronous), and read the per-channel sum /
+//   sum-of-squares of the block back from the slab for the following InstanceNorm: one partial row per
+//   (tile, warp), reduced in a fixed order by the last arriver (StatSink, common.cuh) -- no atomics on data.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "umma.cuh"
-#include "apply_device.cuh"
 
 namespace ap {
 
@@ -50,25 +52,18 @@ struct alignas(64) UmmaParams {
   int kchunks, last_ksteps, cin_off;
   int tiles_x, tiles_y, TW, TH, stride;
   int out_coff;
-  double* stats;
-  int stat_C, stat_coff;
+  StatSink sink;            // InstanceNorm statistics of the output (sink.stats null: none)
+  int slot_mul, slot_add;   // partial row of (tile t of the image, epilogue warp q) = (4 t + q) * slot_mul + slot_add
   // item list in units of tile GROUPS (CG consecutive 128-pixel tiles, one per CTA of the pair):
   // n_full whole groups with bn = Cout, then (groups - n_full) * split N-parts
   int n_full, split, n_items;
   int l2_hints;  // bit 0: raw output stores evict_last (AP_NETG_L2_HINTS)
-  FlagWait wait;         // pair kernel: per-image readiness of the input activations (flag sync), or {null, 0}
-  uint32_t* done_flags;  // pair kernel: += 32-column blocks finished per image, or null
-  // FUSED variant: eight extra warps run the InstanceNorm apply pass of THIS conv's output inside the same CTAs, image
-  // by image as done_flags says the image is complete -- the HBM-bound pass hides under the tensor-bound one, and being
-  // warps of the same resident CTAs they can never be starved of an SM the way a separate spinning kernel can.
-  ApplyP fuse;
   int dbg;  // timing diagnostics only (AP_UMMA_DBG): 1 = no TMA loads after the first fill, 2 = no output stores, 4 = no statistics
 };
 
 struct UmmaConv {
   UmmaParams p;
   int BN, nprod, cg;
-  bool fused;
   dim3 grid;
   size_t smem;
 };
@@ -93,44 +88,24 @@ struct UmmaCfg {
   static constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
   static constexpr int STAGES_RAW = (226 * 1024 - 2 * 4 * 4096 - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 + (CG == 1 && BN <= 128 ? 4096 : 0);
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
 
 struct Item {
   int img, ty, tx, n0, bn;
 };
 
-// Local item `li` of execution unit `unit` (CTA, or CTA pair) -> global item index, or -1 when the unit is done.
-// STRIDED: item = unit + li * nunits (neighbouring CTAs work on neighbouring tiles).  CONTIGUOUS (used where the
-// InstanceNorm statistics are accumulated on chip): the whole-wave part of the item list is dealt in runs, unit u
-// owning [u*K, (u+1)*K), so that consecutive items of a unit lie in the same image; tail items stay strided.
-template <bool CONTIGUOUS>
-__device__ __forceinline__ int item_at(const UmmaParams& p, int li, int unit, int nunits, int K) {
-  if (!CONTIGUOUS) {
-    const int it = unit + li * nunits;
-    return it < p.n_items ? it : -1;
-  }
-  if (li < K) return unit * K + li;
-  const int it = p.n_full + (li - K) * nunits + unit;
+// Local item `li` of execution unit `unit` (CTA, or CTA pair) -> global item index, or -1 when the unit is done:
+// neighbouring units work on neighbouring tiles.
+__device__ __forceinline__ int item_at(const UmmaParams& p, int li, int unit, int nunits) {
+  const int it = unit + li * nunits;
   return it < p.n_items ? it : -1;
 }
 
-// Per-warp accumulation of the InstanceNorm statistics in shared memory across the items of one image: one fp64
-// atomic per (channel, warp, image run) instead of one per (channel, warp, tile).  fp64 atomics on one address
-// serialise in L2 (~15-30 ns each); layers with few channels and thousands of tiles were bound by exactly that
-// (profiles/r01_stat_atomics.md: 128->64 transposed conv 307 -> 138 us without statistics).
+// Phase-packed transposed convs: the column blocks of one item that belong to different output phases fold onto the
+// same channel; each epilogue warp folds them in shared memory (column order) before it stores its partial row.
 constexpr int STAT_ACC_COLS = 128;
 constexpr int STAT_ACC_BYTES = 4 * 2 * STAT_ACC_COLS * 4;  // 4 epilogue warps x {sum, sumsq} x 128 channels x fp32
-
-__device__ __forceinline__ void stat_flush(float* sacc, double* stats, int stat_C, int stat_coff, int img, int ncols, int lane) {
-  for (int c = lane; c < ncols; c += 32) {
-    double* dst = stats + ((size_t)img * stat_C + stat_coff + c) * 2;
-    atomicAdd(dst, (double)sacc[c]);
-    atomicAdd(dst + 1, (double)sacc[STAT_ACC_COLS + c]);
-    sacc[c] = 0.f;
-    sacc[STAT_ACC_COLS + c] = 0.f;
-  }
-}
 
 // ---- single-CTA kernel (cta_group::1): one CTA per 128-pixel tile; used for the N <= 128 layers ----
 __device__ __forceinline__ Item decode_item1(const UmmaParams& p, int item, int BN) {
@@ -169,9 +144,6 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = p.ntaps * p.kchunks;
-  constexpr bool ACC = BN <= STAT_ACC_COLS;  // statistics accumulated on chip, contiguous item runs
-  const int Krun = ACC ? p.n_full / (int)gridDim.x : 0;
-  float* sacc_all = reinterpret_cast<float*>(epi_gen + EPI_BYTES + 256);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
@@ -207,7 +179,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     if (lane == 0) {
       uint32_t cnt = 0;
       for (int li = 0;; ++li) {
-        const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
+        const int item = item_at(p, li, blockIdx.x, gridDim.x);
         if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
@@ -242,7 +214,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     if (lane == 0) {
       uint32_t cnt = 0, local = 0;
       for (int li = 0;; ++li, ++local) {
-        const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
+        const int item = item_at(p, li, blockIdx.x, gridDim.x);
         if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
@@ -295,50 +267,32 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
     const uint64_t opol = (p.l2_hints & 1) ? l2_policy_evict_last() : 0;  // raw output is re-read by the next kernel
     uint32_t local = 0, blk = 0;
-    float* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
-    int simg = -1;
-    if (ACC) {
-      for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0.f;
-      __syncwarp();
-    }
     for (int li = 0;; ++li, ++local) {
-      const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
+      const int item = item_at(p, li, blockIdx.x, gridDim.x);
       if (item < 0) break;
       const Item w = decode_item1(p, item, BN);
-      const bool acc_item = ACC && w.bn == BN;  // N-split tail items use direct atomics
-      if (ACC && simg >= 0 && (w.img != simg || !acc_item)) {
-        stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, BN, lane);
-        simg = -1;
-      }
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
       const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
-      double* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + w.n0 + lane) * 2 : nullptr;
+      const int srow = ((w.ty * p.tiles_x + w.tx) * 4 + q) * p.slot_mul + p.slot_add;
 #pragma unroll 1
       for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
         epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[0], p.out_coff + w.n0 + c0, ox, oy, w.img, opol);
-        if (strow != nullptr) {
+        if (p.sink.stats != nullptr) {
           float cs, cq;
           slab_colsums(slab_gen + sl, lane, &cs, &cq);
-          if (acc_item) {
-            sacc[c0 + lane] += cs;
-            sacc[STAT_ACC_COLS + c0 + lane] += cq;
-            simg = w.img;
-          } else {
-            atomicAdd(strow + (size_t)c0 * 2, (double)cs);
-            atomicAdd(strow + (size_t)c0 * 2 + 1, (double)cq);
-          }
+          stat_put(p.sink, w.img, srow, w.n0 + c0, lane, cs, cq);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
+      if (p.sink.stats != nullptr) stat_arrive(p.sink, w.img, w.n0, w.bn >> 5, lane);
     }
-    if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, BN, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
   }
   tc_fence_before();
@@ -373,9 +327,10 @@ __device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int B
 
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) runs tcgen05.mma.cta_group::2
 // with M = 256; each CTA stages its own A tile and half of the weight tile, the leader (cluster rank 0) issues.
-// PACKED (phase-packed transposed convs): statistics accumulated on chip over contiguous item runs, one staging slab.
-template <int BN, int NPROD, int CG, bool PACKED, bool FUSED>
-__global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
+// PACKED (phase-packed transposed convs): the phases of an item fold onto the same channels before the statistics
+// row is stored; one staging slab.
+template <int BN, int NPROD, int CG, bool PACKED>
+__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   using Cfg = UmmaCfg<BN, NPROD, CG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int PLANES = Cfg::PLANES;
@@ -386,7 +341,6 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
   uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
   constexpr int EPI_SLABS = PACKED ? 1 : EpiCfg<BN>::SLABS;
   constexpr int EPI_BYTES = 4 * EPI_SLABS * 4096;
-  constexpr bool ACC = PACKED;
   const uint32_t bars = epi_s + EPI_BYTES;
   // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);
@@ -396,7 +350,6 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // pair (or CTA) index
   const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int Krun = ACC ? p.n_full / nunits : 0;
   float* sacc_all = reinterpret_cast<float*>(epi_gen + EPI_BYTES + 256);
 
   if (warp == 0 && lane == 0) {
@@ -441,18 +394,10 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
     if (lane == 0) {
       const uint32_t full0 = (CG == 2) ? mapa_rank(bars, 0) : bars;  // full barriers live in the leader
       uint32_t cnt = 0;
-      int ready_img = -1;
       for (int li = 0;; ++li) {
-        const int item = item_at<ACC>(p, li, unit, nunits, Krun);
+        const int item = item_at(p, li, unit, nunits);
         if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, rank);
-        if (p.wait.flags != nullptr && w.img != ready_img) {
-          // the apply pass that produces this image's operands runs concurrently (flag sync): wait for it, then make
-          // its generic-proxy writes visible to the TMA loads below
-          flag_wait(p.wait.flags + w.img, p.wait.expected);
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          ready_img = w.img;
-        }
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
         const int wrows = w.bn / CG;
         const int nbox = wrows / Cfg::W_BOX;
@@ -497,7 +442,7 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
     if (lane == 0 && rank == 0) {
       uint32_t cnt = 0, local = 0;
       for (int li = 0;; ++li, ++local) {
-        const int item = item_at<ACC>(p, li, unit, nunits, Krun);
+        const int item = item_at(p, li, unit, nunits);
         if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, 0);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
@@ -554,7 +499,7 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row0 = q * 32;
@@ -565,25 +510,20 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
     const uint64_t opol = (p.l2_hints & 1) ? l2_policy_evict_last() : 0;  // raw output is re-read by the next kernel
     uint32_t local = 0, blk = 0;
     float* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
-    int simg = -1;
-    if (ACC) {
+    if (PACKED) {
       for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0.f;
       __syncwarp();
     }
     for (int li = 0;; ++li, ++local) {
-      const int item = item_at<ACC>(p, li, unit, nunits, Krun);
+      const int item = item_at(p, li, unit, nunits);
       if (item < 0) break;
       const Item w = decode_item(p, item, BN, CG, rank);
-      const bool acc_item = ACC && p.phase_cols > 0 && p.phase_cols <= STAT_ACC_COLS;
-      if (ACC && simg >= 0 && w.img != simg) {
-        stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
-        simg = -1;
-      }
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
       const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
-      double* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + lane) * 2 : nullptr;
+      const int srow = ((w.ty * p.tiles_x + w.tx) * 4 + q) * p.slot_mul + p.slot_add;
+      const bool want_stats = p.sink.stats != nullptr && !AP_DBG(p.dbg & 4);
 #pragma unroll 1
       for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
         float v[32];
@@ -594,16 +534,14 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
         if (p.phase_cols) { phs = ch / p.phase_cols; ch -= phs * p.phase_cols; }
         if (!AP_DBG(p.dbg & 2))
           epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[phs], p.out_coff + ch, ox, oy, w.img, opol);
-        if (strow != nullptr && !AP_DBG(p.dbg & 4)) {
+        if (want_stats) {
           float cs, cq;
           slab_colsums(slab_gen + sl, lane, &cs, &cq);
-          if (acc_item) {  // the phases of a packed transposed conv fold onto the same channel
+          if (PACKED) {  // the phases of a packed transposed conv fold onto the same channel, in column order
             sacc[ch + lane] += cs;
             sacc[STAT_ACC_COLS + ch + lane] += cq;
-            simg = w.img;
           } else {
-            atomicAdd(strow + (size_t)ch * 2, (double)cs);
-            atomicAdd(strow + (size_t)ch * 2 + 1, (double)cq);
+            stat_put(p.sink, w.img, srow, ch, lane, cs, cq);
           }
         }
       }
@@ -613,27 +551,22 @@ __global__ void __launch_bounds__(FUSED ? 192 + AF_THREADS : 192, 1) conv_umma_k
         if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * acc);
         else mbar_arrive(bars + 144 + 8 * acc);
       }
-      if (p.done_flags != nullptr) {
-        // this warp's share of the item (bn/32 column blocks of 32 rows) has landed: stores complete, statistics added
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          bulk_wait<0>();
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __threadfence();
-          flag_add(p.done_flags + w.img, (uint32_t)(w.bn >> 5));
+      if (want_stats) {
+        if (PACKED) {  // packed items are never split along N: all phases of the tile are in this item
+          const int nblk = p.phase_cols >> 5;
+          for (int b = 0; b < nblk; ++b) {
+            stat_put(p.sink, w.img, srow, 32 * b, lane, sacc[32 * b + lane], sacc[STAT_ACC_COLS + 32 * b + lane]);
+            sacc[32 * b + lane] = 0.f;
+            sacc[STAT_ACC_COLS + 32 * b + lane] = 0.f;
+          }
+          stat_arrive(p.sink, w.img, 0, nblk, lane);
+        } else {
+          stat_arrive(p.sink, w.img, w.n0, w.bn >> 5, lane);
         }
       }
     }
-    if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
     __syncwarp();
-  } else if (FUSED) {
-    // ===================== fused InstanceNorm apply (warps 6..13) =====================
-    const int tid = (int)threadIdx.x - 192;
-    if (p.fuse.raw2) apply_flag_items<1, 8>(p.fuse, tid, (int)blockIdx.x, (int)gridDim.x);
-    else if (p.fuse.res_in) apply_flag_items<2, 8>(p.fuse, tid, (int)blockIdx.x, (int)gridDim.x);
-    else apply_flag_items<0, 8>(p.fuse, tid, (int)blockIdx.x, (int)gridDim.x);
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // the peer's shared memory / barriers stay valid until both CTAs are done
@@ -655,7 +588,7 @@ static int g_sms = 0;
 
 template <int BN, int NPROD, bool PACKED>
 constexpr size_t pair_smem() {
-  return UmmaCfg<BN, NPROD, 2>::SMEM - (PACKED ? (size_t)(EpiCfg<BN>::BYTES - 4 * 4096) - 4096 : 0);
+  return UmmaCfg<BN, NPROD, 2>::SMEM - (PACKED ? (size_t)(EpiCfg<BN>::BYTES - 4 * 4096) : 0) + (PACKED ? STAT_ACC_BYTES : 0);
 }
 
 static int g_dbg = 0;
@@ -666,40 +599,75 @@ template <int BN, int NPROD>
 static int set_attr() {
   AP_CUDA(cudaFuncSetAttribute(conv_umma1_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)UmmaCfg<BN, NPROD, 1>::SMEM));
-  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)pair_smem<BN, NPROD, false>()));
   if (BN == 256)
-    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, NPROD, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, NPROD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pair_smem<256, NPROD, true>()));
-  if (BN == 256 && NPROD == 3)
-    AP_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256, 3, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)pair_smem<256, 3, false>()));
   return AP_OK;
 }
 
+// Function attributes (the opt-in to > 48 KB of dynamic shared memory) belong to a device, not to the process: they are
+// set once for EVERY device a handle or a debug call touches (ap_netg_create(device), ap_conv2d_debug(device)).
+constexpr int AP_MAX_DEVICES = 64;
+static std::mutex g_init_mu;
+static bool g_dev_ready[AP_MAX_DEVICES];
+static int g_dev_pairs[AP_MAX_DEVICES][3][2];  // resident CTA pairs per device, [BN 64/128/256][nprod 1/3]
+
+template <int BN, int NPROD>
+static int count_pairs() {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(g_sms > 0 ? g_sms : 148) & ~1u, 1, 1);
+  cfg.blockDim = dim3(192, 1, 1);
+  cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, 2>::SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2, false>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return n;
+}
+
 int umma_init() {
-  if (g_encode) return AP_OK;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  AP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  AP_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, AP_ERR_CUDA,
-             "cuTensorMapEncodeTiled not available from the driver");
+  std::lock_guard<std::mutex> lock(g_init_mu);
   int dev = 0;
   AP_CUDA(cudaGetDevice(&dev));
-  AP_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  AP_REQUIRE(dev >= 0 && dev < AP_MAX_DEVICES, AP_ERR_UNSUPPORTED, "device ordinal %d", dev);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    AP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    AP_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, AP_ERR_CUDA,
+               "cuTensorMapEncodeTiled not available from the driver");
+    AP_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("AP_NETG_CTA_PAIR");
+    g_pair = e ? atoi(e) : 1;  // 0: never, 1: where it wins (Cout = 256), 2: everywhere
+    const char* lh = getenv("AP_NETG_L2_HINTS");
+    g_l2_hints = lh ? atoi(lh) : 0;
+    const char* d = getenv("AP_UMMA_DBG");
+    g_dbg = d ? atoi(d) : 0;
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  if (g_dev_ready[dev]) return AP_OK;
   AP_TRY((set_attr<64, 1>()));
   AP_TRY((set_attr<128, 1>()));
   AP_TRY((set_attr<256, 1>()));
   AP_TRY((set_attr<64, 3>()));
   AP_TRY((set_attr<128, 3>()));
   AP_TRY((set_attr<256, 3>()));
-  const char* e = getenv("AP_NETG_CTA_PAIR");
-  g_pair = e ? atoi(e) : 1;  // 0: never, 1: where it wins (Cout = 256), 2: everywhere
-  const char* lh = getenv("AP_NETG_L2_HINTS");
-  g_l2_hints = lh ? atoi(lh) : 0;
-  const char* d = getenv("AP_UMMA_DBG");
-  g_dbg = d ? atoi(d) : 0;
-  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  g_dev_pairs[dev][0][0] = count_pairs<64, 1>();  g_dev_pairs[dev][0][1] = count_pairs<64, 3>();
+  g_dev_pairs[dev][1][0] = count_pairs<128, 1>(); g_dev_pairs[dev][1][1] = count_pairs<128, 3>();
+  g_dev_pairs[dev][2][0] = count_pairs<256, 1>(); g_dev_pairs[dev][2][1] = count_pairs<256, 3>();
+  AP_TRY(stem_umma_init_device());
+  AP_TRY(out_umma_init_device());
+  g_dev_ready[dev] = true;
   return AP_OK;
 }
 
@@ -731,42 +699,32 @@ int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C
   return tmap_encode(m, 1, out + ((size_t)py * Wout + px) * C, 4, dims, str, box, es);
 }
 
-// how many CTA pairs of this kernel can be resident at once (74 on a full B200; fewer if a TPC is fused off)
-template <int BN, int NPROD>
-static int max_pairs_of() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(g_sms > 0 ? g_sms : 148) & ~1u, 1, 1);
-  cfg.blockDim = dim3(192, 1, 1);
-  cfg.dynamicSmemBytes = UmmaCfg<BN, NPROD, 2>::SMEM;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<BN, NPROD, 2, false, false>, &cfg) != cudaSuccess || n <= 0) {
-    cudaGetLastError();
-    n = 0;
-  }
-  cached = n;
-  return cached;
-}
-
+// how many CTA pairs of this kernel can be resident at once on the current device (74 on a full B200; fewer if a TPC
+// is fused off); filled in by umma_init
 static int max_pairs(int BN, int nprod) {
-  if (BN == 64) return nprod == 3 ? max_pairs_of<64, 3>() : max_pairs_of<64, 1>();
-  if (BN == 128) return nprod == 3 ? max_pairs_of<128, 3>() : max_pairs_of<128, 1>();
-  return nprod == 3 ? max_pairs_of<256, 3>() : max_pairs_of<256, 1>();
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= AP_MAX_DEVICES || !g_dev_ready[dev]) return 0;
+  return g_dev_pairs[dev][BN == 64 ? 0 : (BN == 128 ? 1 : 2)][nprod == 3 ? 1 : 0];
 }
 
 // `in` must be a bf16 activation. Zero-padded convs address the un-haloed interior (TMA fills
 // out-of-bounds with zeros); reflect-padded ones address the haloed buffer (halo = in.pad >= conv pad).
+static int conv_tiling(const ConvGeom& g, int* TW, int* TH) {
+  if (g.Wv % 128 == 0) { *TW = 128; *TH = 1; }
+  else if (g.Wv == 64 && g.Hv % 2 == 0) { *TW = 64; *TH = 2; }
+  else { set_error("umma conv: virtual grid %dx%d not tileable", g.Hv, g.Wv); return AP_ERR_UNSUPPORTED; }
+  return AP_OK;
+}
+
+int umma_conv_stat_rows(const ConvGeom& g) {
+  int TW = 0, TH = 0;
+  if (conv_tiling(g, &TW, &TH) != AP_OK) return 0;
+  return (g.Wv / TW) * (g.Hv / TH) * 4;
+}
+
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
-                     const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, double* stats,
-                     int stat_C, int stat_coff, const PhasePack* pk, FlagWait wait, uint32_t* done_flags, const ApplyP* fuse) {
+                     const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, const StatSink& sink,
+                     int slot_mul, int slot_add, const PhasePack* pk) {
   AP_TRY(umma_init());
   AP_REQUIRE(in.fmt == FMT_BF16X2 || in.fmt == FMT_BF16, AP_ERR_INVALID, "umma conv needs bf16 activations");
   AP_REQUIRE(nprod == 1 || (nprod == 3 && in.fmt == FMT_BF16X2 && w_lo), AP_ERR_INVALID, "umma conv: nprod/format");
@@ -777,9 +735,7 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   AP_REQUIRE(!g.reflect || in.pad >= 1, AP_ERR_INVALID, "umma conv: reflect padding needs a haloed input");
   AP_REQUIRE(out_C % 4 == 0 && out_coff % 4 == 0, AP_ERR_INVALID, "umma conv: output channel layout");
   int TW, TH;
-  if (g.Wv % 128 == 0) { TW = 128; TH = 1; }
-  else if (g.Wv == 64 && g.Hv % 2 == 0) { TW = 64; TH = 2; }
-  else { set_error("umma conv: virtual grid %dx%d not tileable", g.Hv, g.Wv); return AP_ERR_UNSUPPORTED; }
+  AP_TRY(conv_tiling(g, &TW, &TH));
   AP_REQUIRE(TW * g.stride <= 256, AP_ERR_UNSUPPORTED, "umma conv: TMA box too wide");
 
   UmmaConv* c = new UmmaConv();
@@ -842,33 +798,26 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   p.tiles_x = g.Wv / TW; p.tiles_y = g.Hv / TH;
   p.stride = g.stride;
   p.out_coff = out_coff;
-  p.stats = (g_dbg & 8) ? nullptr : stats;  // AP_UMMA_DBG bit 3 (timing probe only): no InstanceNorm statistics at all
-  p.stat_C = stat_C; p.stat_coff = stat_coff;
+  p.sink = sink;
+  if (g_dbg & 8) p.sink.stats = nullptr;  // AP_UMMA_DBG bit 3 (timing probe only): no InstanceNorm statistics at all
+  p.slot_mul = slot_mul; p.slot_add = slot_add;
+  if (sink.stats != nullptr) {
+    AP_REQUIRE(sink.part && sink.count && sink.C % 32 == 0 && sink.coff % 32 == 0 && slot_add < slot_mul &&
+                   sink.np == (g.Wv / TW) * (g.Hv / TH) * 4 * slot_mul,
+               AP_ERR_INVALID, "umma conv: statistics sink (C=%d coff=%d np=%d, %d tiles x %d)", sink.C, sink.coff, sink.np,
+               (g.Wv / TW) * (g.Hv / TH), slot_mul);
+  }
   // item list: whole waves of full tile groups, the remainder split along N so the tail fills the machine
   const int groups = ntiles / c->cg;
   const int G = c->cg == 2 ? pairs : (g_sms > 0 ? g_sms : 148);  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
   const int rem = groups % G;
   int split = 1;
-  if (rem > 0) {
+  if (rem > 0 && !pk) {  // packed items stay whole: their phases fold onto the same channels inside one epilogue warp
     while (split < 4 && rem * split * 2 <= G && wrows / (split * 2) >= 64) split *= 2;
   }
   p.split = split;
   p.dbg = g_dbg;
   p.l2_hints = g_l2_hints;
-  AP_REQUIRE((wait.flags == nullptr && done_flags == nullptr) || (c->cg == 2 && !pk), AP_ERR_UNSUPPORTED,
-             "flag sync is implemented in the (unpacked) CTA-pair kernel only");
-  p.wait = wait;
-  p.done_flags = done_flags;
-  c->fused = false;
-  if (fuse) {
-    AP_REQUIRE(c->cg == 2 && !pk && nprod == 3 && g.Cout == 256 && done_flags != nullptr && fuse->C == 256, AP_ERR_UNSUPPORTED,
-               "fused apply needs the 3-product N = 256 CTA-pair kernel and completion flags");
-    p.fuse = *fuse;
-    p.fuse.wait0 = FlagWait{done_flags, umma_conv_done_per_image(c)};
-    p.fuse.wait1 = FlagWait{nullptr, 0};
-    p.fuse.done_flags = nullptr;
-    c->fused = true;
-  }
   p.n_full = groups - rem;
   p.n_items = p.n_full + rem * split;
   c->grid = dim3((unsigned)((p.n_items < G ? p.n_items : G) * c->cg), 1);
@@ -878,18 +827,7 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
 
 bool umma_pairs_available() { return umma_init() == AP_OK && g_pair != 0 && max_pairs(256, 3) > 0; }
 
-int umma_pair_regs_per_cta() {
-  cudaFuncAttributes a;
-  if (cudaFuncGetAttributes(&a, (const void*)conv_umma_kernel<256, 3, 2, false, false>) != cudaSuccess) return 1 << 30;
-  return ((a.numRegs + 7) / 8 * 8) * 32 * ((192 / 32 + 3) / 4 * 4);
-}
-
 void umma_conv_destroy(UmmaConv* c) { delete c; }
-
-// every epilogue warp (4 per CTA) adds bn/32 per item: per image = tiles * 4 * BN/32
-uint32_t umma_conv_done_per_image(const UmmaConv* c) {
-  return (uint32_t)(c->p.tiles_x * c->p.tiles_y) * 4u * (uint32_t)(c->BN / 32);
-}
 
 template <int BN, int NPROD, int CG>
 static int launch_one(const UmmaConv* c, cudaStream_t st) {
@@ -910,11 +848,8 @@ static int launch_one(const UmmaConv* c, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (packed) AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, NPROD, 2, true, false>, c->p));
-    else if (c->fused) {
-      cfg.blockDim = dim3(192 + AF_THREADS, 1, 1);
-      AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, 3, 2, false, true>, c->p));
-    } else AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2, false, false>, c->p));
+    if (packed) AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<256, NPROD, 2, true>, c->p));
+    else AP_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, NPROD, 2, false>, c->p));
   }
   launches_add(1);
   return AP_OK;

@@ -117,66 +117,9 @@ __global__ void __launch_bounds__(256, 3) apply_kernel(const ApplyP p) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Flag-synchronised apply for the 256-channel trunk (see FlagWait in common.cuh).  Persistent: one 256-thread CTA per
-// SM walks (image, 32-pixel chunk) items in image order; before the first item of an image it waits until the conv(s)
-// that produce the image have signalled completion, after every item it signals its own.  It is launched on a side
-// stream and runs UNDER the conv kernel that feeds it.  Progress argument: the consumer conv may occupy every SM and
-// spin on this kernel's flags before this kernel's CTAs are placed, so ONE CTA of this kernel must always fit next to
-// a resident conv CTA: no shared memory, 256 threads x <= 72 registers (18 K of the 64 K registers; a 192-thread conv
-// CTA takes up to 31 K with the 4-warp allocation granularity).  apply_flags_fits() checks it against the compiled
-// kernels; with 512-thread CTAs (37 K) the pair did not fit and the forward dead-locked intermittently.
-// ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __maxnreg__(72) apply_flags_kernel(const ApplyP p) {
-  apply_flag_items<MODE>(p, threadIdx.x, blockIdx.x, gridDim.x);
-}
-
-uint32_t apply_flags_done_per_image(int H, int W) { return (uint32_t)(H * W / AF_PIX); }
-
-// registers one CTA of the flag apply kernel occupies (4-warp allocation granularity, 8-register rounding)
-int apply_flags_regs_per_cta() {
-  int worst = 0;
-  cudaFuncAttributes a;
-  const void* ks[3] = {(const void*)apply_flags_kernel<0>, (const void*)apply_flags_kernel<1>, (const void*)apply_flags_kernel<2>};
-  for (const void* k : ks) {
-    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) return 1 << 30;
-    const int r = ((a.numRegs + 7) / 8 * 8) * 32 * ((AF_THREADS / 32 + 3) / 4 * 4);
-    worst = r > worst ? r : worst;
-  }
-  return worst;
-}
-
-static int g_af_sms = 0;
-
-int launch_apply_flags(const ApplyP& p, cudaStream_t st) {
-  AP_REQUIRE(p.C == 256 && p.raw_C % 4 == 0 && p.raw_coff % 4 == 0, AP_ERR_INVALID, "apply_flags: C=%d", p.C);
-  AP_REQUIRE(p.fmt < 0 || (p.dC % 4 == 0 && p.dcoff % 4 == 0), AP_ERR_INVALID, "apply_flags: dst channel layout");
-  AP_REQUIRE((p.W & (p.W - 1)) == 0 && (p.H * p.W) % AF_PIX == 0 && p.res_fmt < 0, AP_ERR_INVALID, "apply_flags: %dx%d", p.H, p.W);
-  AP_REQUIRE(!(p.raw2 && p.res_in), AP_ERR_INVALID, "apply_flags: shortcut operand and residual stream are exclusive");
-  if (g_af_sms == 0) {
-    int dev = 0;
-    AP_CUDA(cudaGetDevice(&dev));
-    AP_CUDA(cudaDeviceGetAttribute(&g_af_sms, cudaDevAttrMultiProcessorCount, dev));
-    // must be co-resident with conv CTAs that configure the SM for (almost) all-shared-memory: ask for the same
-    // carve-out, an SM has one L1/shared split at a time
-    AP_CUDA(cudaFuncSetAttribute(apply_flags_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    AP_CUDA(cudaFuncSetAttribute(apply_flags_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    AP_CUDA(cudaFuncSetAttribute(apply_flags_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
-  const int total = p.H * p.W / AF_PIX * p.B;
-  const int grid = total < g_af_sms ? total : g_af_sms;
-  if (p.raw2) apply_flags_kernel<1><<<grid, AF_THREADS, 0, st>>>(p);
-  else if (p.res_in) apply_flags_kernel<2><<<grid, AF_THREADS, 0, st>>>(p);
-  else apply_flags_kernel<0><<<grid, AF_THREADS, 0, st>>>(p);
-  AP_CUDA(cudaGetLastError());
-  launches_add(1);
-  return AP_OK;
-}
-
 // An SM has ONE L1 / shared-memory split at a time.  The persistent convs configure it for (almost) all shared memory;
-// a kernel that prefers another split may not become co-resident with them.  The flag-synchronised apply kernel MUST be
-// co-resident and always asks for the max-shared carve-out; for the ordinary side-stream kernels it is an option.
+// a kernel that prefers another split may not become co-resident with them; asking for the same carve-out is an option
+// for the side-stream kernels.
 bool carveout_enabled() {  // AP_NETG_CARVEOUT=1 (A/B): measured 1-2 % SLOWER overall -- the elementwise kernels lose their L1
   static int v = -1;      // and the side-stream kernels overlap the convs about as well without it -- so it is off by default
   if (v < 0) { const char* e = getenv("AP_NETG_CARVEOUT"); v = (e && e[0] == '1'); }
@@ -198,8 +141,7 @@ static void apply_carveouts() {
 
 template <int TPP>
 static void launch_apply_tpp(const ApplyP& p, dim3 grid, cudaStream_t st) {
-  static bool once = false;
-  if (!once) { apply_carveouts<TPP>(); once = true; }
+  apply_carveouts<TPP>();  // no-op unless AP_NETG_CARVEOUT=1; function attributes are per device, so not cached
   static int deep = -1;  // AP_NETG_APPLY_DEEP=0: the two-round MODE 0 kernel (A/B)
   if (deep < 0) { const char* e = getenv("AP_NETG_APPLY_DEEP"); deep = !(e && e[0] == '0'); }
   if (p.raw2) apply_kernel<TPP, 1, 4><<<grid, 256, 0, st>>>(p);
@@ -314,9 +256,9 @@ __global__ void __launch_bounds__(256) warp_kernel(const WarpP p) {
     const int pix = pix_base + lp;
     const int logS = 31 - __clz(S);
     const int i = pix >> logS, j = pix & (S - 1);
-    const float* mo = p.motion + (size_t)n * 256 * 256 * 2;
-    const float* fl = p.flow + (size_t)n * 2 * 256 * 256;
-    const float* ms = p.ifmask + (size_t)n * 256 * 256;
+    const float* mo = p.io->motion + (size_t)n * 256 * 256 * 2;
+    const float* fl = p.io->flow + (size_t)n * 2 * 256 * 256;
+    const float* ms = p.io->ifmask + (size_t)n * 256 * 256;
     Lerp ly{}, lx{};
     if (p.level > 0) {
       const float scale = 255.f / (float)(S - 1);  // fp32((in-1)/(out-1))
@@ -404,16 +346,24 @@ int launch_warp(const WarpP& p, cudaStream_t st) {
   AP_REQUIRE(p.C == 32 || p.C == 64 || p.C == 128, AP_ERR_INVALID, "warp: C=%d", p.C);
   AP_REQUIRE((p.S & (p.S - 1)) == 0 && (p.S * p.S) % WARP_PIX == 0, AP_ERR_INVALID, "warp: S=%d", p.S);
   dim3 grid(p.S * p.S / WARP_PIX, p.B);
-  static bool once = false;
-  if (!once) {
-    prefer_max_shared(warp_kernel<8>);
-    prefer_max_shared(warp_kernel<16>);
-    prefer_max_shared(warp_kernel<32>);
-    once = true;
-  }
+  prefer_max_shared(warp_kernel<8>);  // no-op unless AP_NETG_CARVEOUT=1
+  prefer_max_shared(warp_kernel<16>);
+  prefer_max_shared(warp_kernel<32>);
   if (p.C == 32) warp_kernel<8><<<grid, 256, 0, st>>>(p);
   else if (p.C == 64) warp_kernel<16><<<grid, 256, 0, st>>>(p);
   else warp_kernel<32><<<grid, 256, 0, st>>>(p);
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  return AP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pointer table of the caller's tensors (IoPtrs, common.cuh)
+// ------------------------------------------------------------------------------------------------
+__global__ void set_io_kernel(IoPtrs* dst, const IoPtrs v) { *dst = v; }
+
+int launch_set_io(IoPtrs* dst, const IoPtrs& v, cudaStream_t st) {
+  set_io_kernel<<<1, 1, 0, st>>>(dst, v);
   AP_CUDA(cudaGetLastError());
   launches_add(1);
   return AP_OK;

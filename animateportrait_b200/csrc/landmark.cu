@@ -20,11 +20,13 @@ bool carveout_enabled();
 // channel loops fully unrolled every FMA reads its weight straight from the constant bank, no load at all.
 template <int CIN, int COUT>
 struct LandP {
-  const float* in0;   // CIN == 1: land1 [B1,1,256,256];  else raw NHWC [B1+B2,Hin,Win,CIN]
-  const float* in1;   // CIN == 1: land2 [B2,1,256,256]
+  const IoPtrs* io;   // CIN == 1: io->land1 [B1,1,256,256], io->land2 [B2,1,256,256] of the caller
+  const float* in0;   // CIN > 1: raw NHWC [B1+B2,Hin,Win,CIN]
   const double* in_stats;  // [B1+B2][CIN][2] (CIN > 1)
   float* out;         // raw NHWC [B1+B2,Hout,Wout,COUT]
   double* out_stats;  // [B1+B2][COUT][2]
+  float* part;        // [B1+B2][CTAs per image][2*COUT]: per-CTA {sums, sums of squares}, reduced in CTA order by the
+  uint32_t* count;    // [B1+B2] tickets                   last CTA of the image (deterministic, see StatSink)
   int B, Hin, Hout;   // B = B1, the number of land1 maps (the batch size, or 1 in clip mode: one source landmark map)
   float w[9 * CIN * COUT];
 };
@@ -32,14 +34,14 @@ struct LandP {
 template <int CIN, int COUT, int STRIDE>
 __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ LandP<CIN, COUT> p) {
   __shared__ float s_mean[CIN], s_rstd[CIN];
-  __shared__ float s_red[2 * COUT];
+  __shared__ float s_red[8][2 * COUT];
+  __shared__ uint32_t s_ticket;
   const int tid = threadIdx.x;
   const int HWo = p.Hout * p.Hout;
   const int gpix = blockIdx.x * 256 + tid;  // Hout*Hout is a multiple of 256: one image per CTA
   const int n = gpix / HWo;
   const int pix = gpix - n * HWo;
   const int oy = pix / p.Hout, ox = pix - oy * p.Hout;
-  if (tid < 2 * COUT) s_red[tid] = 0.f;
   if (CIN > 1 && tid < CIN) {
     const double inv = 1.0 / (double)(p.Hin * p.Hin);
     const double su = p.in_stats[((size_t)n * CIN + tid) * 2 + 0];
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
       if (ix < 0 || ix >= p.Hin) continue;
       const float* wt = p.w + (ky * 3 + kx) * CIN * COUT;
       if (CIN == 1) {
-        const float* src = (n < p.B) ? p.in0 + (size_t)n * p.Hin * p.Hin : p.in1 + (size_t)(n - p.B) * p.Hin * p.Hin;
+        const float* src = (n < p.B) ? p.io->land1 + (size_t)n * p.Hin * p.Hin : p.io->land2 + (size_t)(n - p.B) * p.Hin * p.Hin;
         const float v = __ldg(src + iy * p.Hin + ix);
 #pragma unroll
         for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wt[o], acc[o]);
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
 #pragma unroll
   for (int o4 = 0; o4 < COUT / 4; ++o4) dst[o4] = make_float4(acc[o4 * 4], acc[o4 * 4 + 1], acc[o4 * 4 + 2], acc[o4 * 4 + 3]);
 
-  // per-channel sum / sum of squares: warp shuffle tree, then one shared atomic per warp and channel
+  // per-channel sum / sum of squares in a fixed order: warp shuffle tree, the 8 warps of the CTA in warp order, the
+  // CTAs of the image in CTA order (by whichever CTA finishes last)
 #pragma unroll
   for (int o = 0; o < COUT; ++o) {
     float s = acc[o], q = acc[o] * acc[o];
@@ -101,44 +104,62 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
       q += __shfl_xor_sync(0xffffffffu, q, d);
     }
     if ((tid & 31) == 0) {
-      atomicAdd(&s_red[o], s);
-      atomicAdd(&s_red[COUT + o], q);
+      s_red[tid >> 5][o] = s;
+      s_red[tid >> 5][COUT + o] = q;
     }
   }
   __syncthreads();
+  const int ctas = HWo / 256;
+  const int cta = blockIdx.x - n * ctas;
   if (tid < 2 * COUT) {
-    const int which = tid / COUT, c = tid - which * COUT;
-    atomicAdd(p.out_stats + ((size_t)n * COUT + c) * 2 + which, (double)s_red[tid]);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][tid];
+    p.part[((size_t)n * ctas + cta) * (2 * COUT) + tid] = t;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(p.count + n, 1u);
+  __syncthreads();
+  if (s_ticket == (uint32_t)(ctas - 1)) {
+    __threadfence();
+    if (tid < 2 * COUT) {
+      const int which = tid / COUT, c = tid - which * COUT;
+      const float* src = p.part + (size_t)n * ctas * (2 * COUT) + tid;
+      double t = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < ctas; ++r) t += (double)__ldcg(src + (size_t)r * (2 * COUT));
+      p.out_stats[((size_t)n * COUT + c) * 2 + which] = t;
+    }
+    if (tid == 0) p.count[n] = 0;
   }
 }
 
 // land1 [B1,1,256,256], land2 [B2,1,256,256] -> raw [B1+B2,64,64,16] + stats; r0/r1 are workspace raws (with stats).
 // w0/w1/w2 are HOST arrays in [slab][Cin][Cout] order.
-int launch_landmark_branch(const float* land1, const float* land2, const float* w0, const float* w1, const float* w2,
+int launch_landmark_branch(const IoPtrs* io, const float* w0, const float* w1, const float* w2,
                            const Raw& r0, const Raw& r1, const Raw& r2, int B1, int B2, cudaStream_t st) {
   const int NB = B1 + B2;
   AP_REQUIRE(r0.B == NB && r1.B == NB && r2.B == NB, AP_ERR_INVALID, "landmark: workspace batch");
-  static bool once = false;
-  if (!once && carveout_enabled()) {  // co-residency with the stem kernel's all-shared-memory SM configuration (see elementwise.cu)
+  if (carveout_enabled()) {  // co-residency with the stem kernel's all-shared-memory SM configuration (see elementwise.cu)
     cudaFuncSetAttribute(land_conv_kernel<1, 8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(land_conv_kernel<8, 16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(land_conv_kernel<16, 16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    once = true;
   }
   {
-    LandP<1, 8> a{land1, land2, nullptr, r0.p, r0.stats, B1, 256, 256, {}};
+    LandP<1, 8> a{io, nullptr, nullptr, r0.p, r0.stats, reinterpret_cast<float*>(r0.part), r0.count, B1, 256, 256, {}};
     memcpy(a.w, w0, sizeof(a.w));
     land_conv_kernel<1, 8, 1><<<NB * 65536 / 256, 256, 0, st>>>(a);
     AP_CUDA(cudaGetLastError());
   }
   {
-    LandP<8, 16> b{r0.p, nullptr, r0.stats, r1.p, r1.stats, B1, 256, 128, {}};
+    LandP<8, 16> b{nullptr, r0.p, r0.stats, r1.p, r1.stats, reinterpret_cast<float*>(r1.part), r1.count, B1, 256, 128, {}};
     memcpy(b.w, w1, sizeof(b.w));
     land_conv_kernel<8, 16, 2><<<NB * 16384 / 256, 256, 0, st>>>(b);
     AP_CUDA(cudaGetLastError());
   }
   {
-    LandP<16, 16> c{r1.p, nullptr, r1.stats, r2.p, r2.stats, B1, 128, 64, {}};
+    LandP<16, 16> c{nullptr, r1.p, r1.stats, r2.p, r2.stats, reinterpret_cast<float*>(r2.part), r2.count, B1, 128, 64, {}};
     memcpy(c.w, w2, sizeof(c.w));
     land_conv_kernel<16, 16, 2><<<NB * 4096 / 256, 256, 0, st>>>(c);
     AP_CUDA(cudaGetLastError());

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -104,14 +105,56 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
             nn.Conv2d(1, 8, 3, padding=1), nl(8), nn.ReLU(True),
             nn.Conv2d(8, con, 3, stride=2, padding=1), nl(con), nn.ReLU(True),
             nn.Conv2d(con, con, 3, stride=2, padding=1), nl(con))
+        self._options: Dict[str, int] = {}
+        self._reset_native()
+
+    # ---- the native handle --------------------------------------------------------------------------
+    # The handle belongs to ONE module object.  Copies made behind the module's back share its __dict__ entries
+    # (nn.DataParallel.replicate: replica.__dict__ = self.__dict__.copy(); copy.copy) or cannot carry a ctypes pointer
+    # (copy.deepcopy, pickle): every such copy starts without a handle and creates its own on first use, and the handle
+    # is destroyed by a finalizer tied to the object that created it, never by a replica.
+    def _reset_native(self):
         self._handle: Optional[C.c_void_p] = None
         self._handle_device: Optional[int] = None
+        self._handle_owner: int = id(self)
+        self._finalizer = None
         self._dirty = True
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_weights_dirty())
+        self._weights_seen = None
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._reset_native()
+        return replica
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in ("_handle", "_handle_device", "_finalizer", "_weights_seen"):
+            state[k] = None
+        state["_dirty"] = True
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._handle_owner = id(self)
+
+    @staticmethod
+    def _destroy(handle):
+        try:
+            _capi.lib().ap_netg_destroy(handle)
+        except Exception:
+            pass
+
+    def _release(self):
+        if self.__dict__.get("_handle") is not None and self.__dict__.get("_handle_owner") == id(self):
+            fin = self.__dict__.get("_finalizer")
+            if fin is not None:
+                fin()  # runs _destroy once
+        self._handle, self._finalizer = None, None
 
     # ---- weight synchronisation with the library -------------------------------------------------
     def mark_weights_dirty(self):
-        """Call after changing parameters in place; load_state_dict / .to() / .cuda() do it themselves."""
+        """Forces a re-upload at the next call.  Not needed after load_state_dict / .to() / in-place parameter changes
+        (optimizer steps, net.apply(init_func), p.data.copy_): those are detected through the tensors' version counters."""
         self._dirty = True
 
     def _apply(self, fn, *a, **k):
@@ -119,29 +162,45 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
         self._dirty = True
         return r
 
-    def _release(self):
-        if self.__dict__.get("_handle") is not None:
-            try:
-                _capi.lib().ap_netg_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
+    def _weight_tensors(self):
+        """(checkpoint key, tensor) of the 74 conv weights / biases.  Walks the children instead of state_dict():
+        DataParallel replicas carry their broadcast copies as plain attributes, not as registered parameters."""
+        for name, m in self.named_modules():
+            for pn in ("weight", "bias"):
+                t = getattr(m, pn, None)
+                if isinstance(t, torch.Tensor):
+                    yield f"{name}.{pn}", t
 
-    def __del__(self):
-        self._release()
+    def _weights_signature(self):
+        # (storage address, in-place version) of every parameter: changes whenever a parameter is rebound or written
+        return tuple((t.data_ptr(), t._version) for _, t in self._weight_tensors())
+
+    def set_option(self, name: str, value: int) -> None:
+        """Execution options of the native handle (`ap_netg_set_option`): graphs, overlap, keep_intermediates."""
+        self._options[name] = int(value)
+        if self._handle is not None:
+            _capi.check(_capi.lib().ap_netg_set_option(self._handle, name.encode(), int(value)), "ap_netg_set_option")
 
     def _sync(self, device: torch.device):
         lib = _capi.lib()
         idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self.__dict__.get("_handle_owner") != id(self):  # a shallow copy of another module: never touch its handle
+            self._reset_native()
         if self._handle is None or self._handle_device != idx:
             self._release()
             h = C.c_void_p()
             _capi.check(lib.ap_netg_create(C.byref(h), self.output_nc, _capi.PRECISIONS[self.precision], idx),
                         "ap_netg_create")
             self._handle, self._handle_device = h, idx
+            self._finalizer = weakref.finalize(self, ResnetConditionTriGenerator32_full_ifw._destroy, h)
+            for k, v in self._options.items():
+                _capi.check(lib.ap_netg_set_option(h, k.encode(), v), "ap_netg_set_option")
+            self._dirty = True
+        sig = self._weights_signature()
+        if sig != self._weights_seen:
             self._dirty = True
         if self._dirty:
-            sd = self.state_dict()
+            sd = dict(self._weight_tensors())
             keep = []
             names = (C.c_char_p * len(sd))()
             ptrs = (C.c_void_p * len(sd))()
@@ -158,6 +217,7 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
             _capi.check(lib.ap_netg_load_weights(self._handle, len(sd), names, ptrs, shapes, 1, C.c_void_p(stream)),
                         "ap_netg_load_weights")
             self._dirty = False
+            self._weights_seen = sig
 
     # ---- the reference interface ----------------------------------------------------------------
     def forward(self, input, land1, land2, motion, flow, ifmask):

@@ -96,7 +96,16 @@ int ap_netg_forward_host(ap_netg* handle, int B, const float* input, const float
 int ap_netg_compose(int device, int B, int output_nc, const float* fake_B, const float* mask, const float* motion,
                     const float* static_B, float* blended, uint8_t* image_u8, void* cuda_stream);
 
-/* Number of kernels of this library launched by the most recent forward on this handle. */
+/* Execution options of a handle (none changes results beyond what is stated):
+ *   "graphs"             1 (default; AP_NETG_GRAPH=0 turns it off): the launch sequence of a batch shape is captured
+ *                        once and replayed as a CUDA graph -- the reference's own call is batch size 1
+ *                        (Module2/test.py:42), where launch overhead dominates; 0: plain stream launches.  Bit-identical.
+ *   "overlap"            1 (default; AP_NETG_OVERLAP=0): independent branches of the graph run concurrently.  Bit-identical.
+ *   "keep_intermediates" 0 (default): buffers of dead intermediates are reused; 1: every intermediate keeps its buffer so
+ *                        that ap_netg_debug_read can return any tap after the forward. */
+int ap_netg_set_option(ap_netg* handle, const char* name, int value);
+
+/* Number of kernels of this library launched (or replayed from the graph) by the most recent forward on this handle. */
 int ap_netg_last_launch_count(ap_netg* handle, int64_t* count);
 
 /* Per-kernel-class device timing of the forward (CUDA events on the launch stream, one per launch).

@@ -89,10 +89,12 @@ def test_sharded_clip_equals_single_process(world, T, with_flow, tmp_path):
 # ------------------------------------------------------------------------------------------------------
 # GPU
 # ------------------------------------------------------------------------------------------------------
+UINT8_OFF_BY_ONE_FRACTION = 0.005   # fraction of uint8 pixels allowed to differ from the oracle's by one level
+
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("onc", [1, 3])
-def test_clip_renderer_matches_frame_by_frame_oracle(onc):
+@pytest.mark.parametrize("onc,precision", [(1, "fp32"), (3, "fp32"), (1, "bf16"), (3, "bf16")])
+def test_clip_renderer_matches_frame_by_frame_oracle(onc, precision):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import animateportrait_b200 as ap
@@ -102,15 +104,25 @@ def test_clip_renderer_matches_frame_by_frame_oracle(onc):
     sd = O.make_state_dict(onc, seed=3, bias_std=0.3)
     photo, matte, static, src, seq, flow, ifmask = synth.make_clip(T, output_nc=onc, seed=31 + onc)
     want_f, want_u8 = OC.render_clip_frames(sd, photo, matte, static, src.numpy(), seq.numpy(), flow, ifmask)
-    net = ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3)
+    net = ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3, precision=precision)
     net.module.load_state_dict(sd)
     r = ClipRenderer(net, batch=2)                     # ragged: batches of 2 + 1
     r.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
     got_f = r.render(seq, flow.to(dev), ifmask.to(dev), return_tensor=True).cpu()    # host landmarks are accepted
     got_u8 = r.render(seq.to(dev), flow.to(dev), ifmask.to(dev)).cpu().numpy()
-    assert (got_f - want_f).abs().max().item() <= 1e-3          # north_star's fp32 gate, through the whole frame path
     d = np.abs(got_u8.astype(np.int16) - want_u8.astype(np.int16))
-    assert got_u8.shape == (T, 256, 256, 3) and d.max() <= 1 and (d > 0).mean() <= 0.1
+    assert got_u8.shape == (T, 256, 256, 3)
+    if precision == "bf16":
+        # bf16 convs (BASELINE.json configs[2]): the mode's own stated tolerance, through the whole frame
+        # path; a uint8 level is 2/255 of the [-1,1] range
+        e = (got_f - want_f).abs()
+        assert e.max().item() <= 0.1 and e.mean().item() <= 0.012, (e.max().item(), e.mean().item())
+        assert d.max() <= 14 and d.mean() <= 1.6, (d.max(), d.mean())
+        return
+    assert (got_f - want_f).abs().max().item() <= 1e-3          # north_star's fp32 gate, through the whole frame path
+    # 1e-3 of the [-1,1] range is an eighth of a uint8 level: a frame value within 1e-3 of a rounding boundary may land on
+    # the neighbouring level; measured on B200: 0.05-0.09 % of the pixels (`tools/gpu_check.py` prints the fraction)
+    assert d.max() <= 1 and (d > 0).mean() <= UINT8_OFF_BY_ONE_FRACTION, (d.max(), (d > 0).mean())
     # without matte / static drawing: plain generator frames, zero intrinsic flow and full visibility by default
     r.set_photo(photo.to(dev), src.to(dev))
     plain = r.render(seq[:1].to(dev), return_tensor=True).cpu()
@@ -147,10 +159,10 @@ def test_shared_photo_forward_equals_forward_on_copies_of_the_photo(precision):
         # bf16 mode: a last-bit change of a statistic flips bf16 roundings downstream; two valid bf16 evaluations differ by
         # up to the mode's own error against the oracle (gate 0.1 / mean 0.012, measured 0.047 here), so bound the maximum
         # loosely and the mean as well -- a mis-routed image would be O(1) everywhere
-        tol = 0.25 if precision == "bf16" else 2e-4
+        # tensor-core modes: bit-identical (the InstanceNorm statistics are reduced in a fixed, batch-independent order);
+        # the CUDA-core validation mode accumulates them with atomics
+        tol = 2e-4 if precision == "fp32_simt" else 0.0
         assert (got - want).abs().max().item() <= tol
-        if precision == "bf16":
-            assert (got - want).abs().mean().item() <= 0.03
         for tap in ("tri00", "tri11", "tri22"):                     # photo-only taps are a batch of one in clip mode
             assert net.debug_read(tap).shape[0] == 1
         assert net.debug_read("warp2").shape[0] == B

@@ -15,6 +15,7 @@ from tests.golden.make_golden import CASES
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 FP32_TOL = 1e-3
+TAP_TOL = 1e-3  # per unit of the tap's magnitude
 BF16_MAX, BF16_MEAN = 0.1, 0.012
 
 
@@ -25,11 +26,21 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def _net(onc, sd, dev, precision):
+def _net(onc, sd, dev, precision, keep_intermediates=False):
     net = ap.define_G(3, onc, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3,
                       precision=precision)
     net.module.load_state_dict(sd)
+    if keep_intermediates:  # debug taps of intermediates whose buffers are otherwise reused (block outputs)
+        net.module.set_option("keep_intermediates", 1)
     return net
+
+
+def _same(a, b, precision="fp32"):
+    """Two evaluations of the same frames by the tensor-core modes are bit-identical whatever the batch size, the
+    stream structure or the launch mechanism: the InstanceNorm statistics are reduced in a fixed order (StatSink,
+    csrc/common.cuh).  The CUDA-core validation mode accumulates them with fp64 atomics (order-dependent, <= 2e-4)."""
+    d = (a - b).abs().max().item()
+    return d == 0.0 if precision != "fp32_simt" else d <= 2e-4
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -85,7 +96,7 @@ def _run_case(name, dev, precision, with_taps=False):
     onc, B, wseed, bstd, iseed, kind = CASES[name]
     sd = O.make_state_dict(onc, seed=wseed, bias_std=bstd)
     inputs = O.make_inputs(B, seed=iseed, kind=kind)
-    net = _net(onc, sd, dev, precision)
+    net = _net(onc, sd, dev, precision, keep_intermediates=with_taps)
     with torch.no_grad():
         y = net(*[t.to(dev) for t in inputs])
     torch.cuda.synchronize()
@@ -114,19 +125,22 @@ def test_forward_bf16_within_stated_tolerance(name, dev, golden_dir):
 @pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
 def test_every_intermediate_matches_the_oracle(precision, dev):
     name = "c1_line_bias"
-    net, sd, inputs, y = _run_case(name, dev, precision)
+    net, sd, inputs, y = _run_case(name, dev, precision, with_taps=True)
     taps = {}
     y_ref = O.netg_forward(sd, *inputs, tap=lambda n, v: taps.__setitem__(n, v))
-    report = {}
+    report, scale = {}, {}
     for k, ref in taps.items():
         if k == "pre_tanh":
             continue
         got = net.module.debug_read(k).cpu()
         assert got.shape == ref.shape, k
         report[k] = (got - ref).abs().max().item()
-    report["out"] = (y - y_ref).abs().max().item()
-    bad = {k: v for k, v in report.items() if v > (1e-3 if k == "out" else 5e-3)}
-    assert not bad, f"taps off: {bad}; all: {report}"
+        scale[k] = max(1.0, ref.abs().max().item())
+    report["out"], scale["out"] = (y - y_ref).abs().max().item(), 1.0
+    # every tap at the output's own gate, relative to the tap's magnitude (InstanceNorm'ed taps are O(1); the residual
+    # stream and the un-normalised merge output grow to O(10)): measured <= 2.5e-4 * scale on B200
+    bad = {k: (v, scale[k]) for k, v in report.items() if v > TAP_TOL * scale[k]}
+    assert not bad, f"taps off (err, scale): {bad}; all: {report}"
 
 
 def test_host_buffer_entry_point_and_batch_independence(dev):
@@ -140,8 +154,8 @@ def test_host_buffer_entry_point_and_batch_independence(dev):
     with torch.no_grad():
         y_dev = net(*[t.to(dev) for t in inputs]).cpu()
         y_one = torch.cat([net(*[t[i:i + 1].to(dev) for t in inputs]).cpu() for i in range(B)])
-    assert (y_host - y_dev).abs().max().item() <= 2e-4   # same kernels, same inputs (stat atomics are order-dependent)
-    assert (y_one - y_dev).abs().max().item() <= 2e-4    # frames are independent (InstanceNorm is per sample)
+    assert _same(y_host, y_dev)   # same kernels, same inputs
+    assert _same(y_one, y_dev)    # frames are independent (InstanceNorm is per sample): bit-identical to B=1 calls
     y_ref = O.netg_forward(sd, *[t[3:4] for t in inputs])
     assert (y_dev[3:4] - y_ref).abs().max().item() <= FP32_TOL
 
@@ -158,8 +172,8 @@ def test_full_size_batch16_properties(dev):
         y2 = net(*inputs)
         y_last = net(*[t[15:16] for t in inputs])
     assert torch.isfinite(y1).all() and y1.abs().max().item() <= 1.0
-    assert (y1 - y2).abs().max().item() <= 2e-4  # stat atomics are order-dependent
-    assert (y1[15:16] - y_last).abs().max().item() <= 1e-4
+    assert _same(y1, y2)                 # run-to-run determinism
+    assert _same(y1[15:16], y_last)      # batch of 16 == the frame on its own
     y_ref = O.netg_forward(sd, *[t[15:16].cpu() for t in inputs])
     assert (y_last.cpu() - y_ref).abs().max().item() <= FP32_TOL
 
@@ -175,7 +189,12 @@ def test_weights_can_be_swapped_and_errors_surface(dev):
         net.load_state_dict(sd_a)
         ya2 = net(*inputs)
     assert (ya - yb).abs().max().item() > 1e-2
-    assert (ya - ya2).abs().max().item() <= 2e-4
+    assert _same(ya, ya2)
+    # in-place parameter changes (optimizer steps, net.apply(init_func), weight surgery) are picked up without a hint
+    with torch.no_grad():
+        net.model3[7].bias.add_(0.5)
+        yc = net(*inputs)
+    assert (yc - ya).abs().max().item() > 1e-2
     with torch.no_grad(), pytest.raises(RuntimeError, match="shape"):
         net(inputs[0], inputs[1], inputs[2], inputs[3][:, :128], inputs[4], inputs[5])
     with pytest.raises(RuntimeError, match="inference-only"):
@@ -199,9 +218,9 @@ def test_branch_overlap_on_side_streams_matches_serial_execution(dev, monkeypatc
         with torch.no_grad():
             ys = [net(*inputs).clone() for _ in range(3)]  # repeated: workspace reuse across forwards stays ordered
         torch.cuda.synchronize()
-        assert all((y - ys[0]).abs().max().item() <= 2e-4 for y in ys)
+        assert all(_same(y, ys[0]) for y in ys)
         outs[mode] = ys[-1]
-    assert (outs["1"] - outs["0"]).abs().max().item() <= 2e-4
+    assert _same(outs["1"], outs["0"])
     y_ref = O.netg_forward(sd, *[t[1:2].cpu() for t in inputs])
     assert (outs["1"][1:2].cpu() - y_ref).abs().max().item() <= FP32_TOL
 
@@ -218,12 +237,98 @@ def test_plan_cache_is_bounded_and_eviction_is_transparent(dev):
         free0 = torch.cuda.mem_get_info(dev)[0]
         for b in range(7, 0, -1):                    # 7 more shapes: B=8 and B=7 get evicted
             y = net(*[t[:b] for t in inputs])
-            assert (y - first[:b]).abs().max().item() <= 2e-4
+            assert _same(y, first[:b])
         torch.cuda.synchronize()
         grown = free0 - torch.cuda.mem_get_info(dev)[0]
         kept = sum(net.workspace_bytes(b) for b in range(1, 7))
         # without eviction the library would now hold B=1..7 on top of B=8; with it B=8 (counted in free0) and B=7 are gone
         assert grown < kept - net.workspace_bytes(8) + (1 << 30), (grown, kept)
         again = net(*inputs)                         # re-planned
-        assert (again - first).abs().max().item() <= 2e-4
-        assert net.debug_read("merge").shape[0] == 8
+        assert _same(again, first)
+        assert net.debug_read("tri02").shape[0] == 8
+
+
+# ------------------------------------------------------------------------------------------------------
+# CUDA-graph replay, determinism, the batch sizes the benches run, several devices in one process
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_equals_stream_launches_and_runs_are_bit_identical(precision, dev):
+    """The forward of a batch shape is captured once and replayed as a CUDA graph (option "graphs", default on); the
+    stream-launch path is the same kernels in the same order.  Both, repeated, on different input buffers."""
+    sd = O.make_state_dict(1, seed=9, bias_std=0.2)
+    net = _net(1, sd, dev, precision).module
+    sets = [[t.to(dev) for t in O.make_inputs(2, seed=40 + i, kind="noise" if i else "smooth")] for i in range(2)]
+    with torch.no_grad():
+        g1 = [net(*s_).clone() for s_ in sets]       # first call captures, second replays with other pointers
+        n_graph = net.last_launch_count()
+        g2 = [net(*s_).clone() for s_ in sets]
+        net.set_option("graphs", 0)
+        p1 = [net(*s_).clone() for s_ in sets]
+        n_stream = net.last_launch_count()
+        net.set_option("graphs", 1)
+        g3 = [net(*s_).clone() for s_ in sets]
+    assert n_graph == n_stream and n_graph > 40
+    for a, b, c, d in zip(g1, g2, p1, g3):
+        assert (a - b).abs().max().item() == 0 and (a - c).abs().max().item() == 0 and (a - d).abs().max().item() == 0
+    assert (g1[0] - g1[1]).abs().max().item() > 1e-3   # the replay really read the second input set
+    y_ref = O.netg_forward(sd, *[t[:1].cpu() for t in sets[1]])
+    d = (g1[1][:1].cpu() - y_ref).abs()
+    assert d.max().item() <= (FP32_TOL if precision == "fp32" else BF16_MAX)
+
+
+def test_config3_batch64_line_fp32(dev):
+    """BASELINE.json configs[3] shard size: 64 frames per GPU, output_nc=1, fp32-accurate.  Oracle on the first, a middle
+    and the last frame; every frame of the batch against the same frame run on its own (bit-identical)."""
+    onc, B = 1, 64
+    sd = O.make_state_dict(onc, seed=0)
+    inputs = [t.to(dev) for t in O.make_inputs(B, seed=1016, kind="smooth")]
+    net = _net(onc, sd, dev, "fp32").module
+    with torch.no_grad():
+        y = net(*inputs)
+        ones = torch.cat([net(*[t[i:i + 1] for t in inputs]) for i in range(B)])
+    assert torch.isfinite(y).all()
+    assert (y - ones).abs().max().item() == 0
+    for i in (0, 31, 63):
+        y_ref = O.netg_forward(sd, *[t[i:i + 1].cpu() for t in inputs])
+        assert (y[i:i + 1].cpu() - y_ref).abs().max().item() <= FP32_TOL, i
+
+
+def test_config4_batch32_cartoon_bf16(dev):
+    """BASELINE.json configs[4] shard size: 32 frames per GPU, output_nc=3, bf16 convs, under the bf16 mode's stated
+    tolerance (max-abs 0.1, mean-abs 0.012); batch == frames one by one, bit-identical."""
+    onc, B = 3, 32
+    sd = O.make_state_dict(onc, seed=0)
+    inputs = [t.to(dev) for t in O.make_inputs(B, seed=1019, kind="smooth")]
+    net = _net(onc, sd, dev, "bf16").module
+    with torch.no_grad():
+        y = net(*inputs)
+        ones = torch.cat([net(*[t[i:i + 1] for t in inputs]) for i in range(B)])
+    assert y.shape == (B, 3, 256, 256) and torch.isfinite(y).all()
+    assert (y - ones).abs().max().item() == 0
+    for i in (0, 15, 31):
+        d = (y[i:i + 1].cpu() - O.netg_forward(sd, *[t[i:i + 1].cpu() for t in inputs])).abs()
+        assert d.max().item() <= BF16_MAX and d.mean().item() <= BF16_MEAN, (i, d.max().item(), d.mean().item())
+
+
+def test_handles_on_two_devices_in_one_process():
+    """Kernel attributes (the opt-in to > 48 KB of dynamic shared memory) are per device: a second handle on another GPU
+    of the same process must work, and nn.DataParallel over both devices must give the single-device frames."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    sd = O.make_state_dict(1, seed=3, bias_std=0.1)
+    inputs = O.make_inputs(4, seed=11, kind="smooth")
+    ys = []
+    for d in (0, 1):
+        net = ap.define_G(3, 1, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [d], div=3, disp=3).module
+        net.load_state_dict(sd)
+        with torch.no_grad():
+            ys.append(net(*[t.to(f"cuda:{d}") for t in inputs]).cpu())
+    assert (ys[0] - ys[1]).abs().max().item() == 0
+    net = ap.ResnetConditionTriGenerator32_full_ifw(3, 1, 64, norm_layer=ap.get_norm_layer("instance"), n_blocks=9, div=3,
+                                                    disp=3).to("cuda:0")
+    net.load_state_dict(sd)
+    dp = torch.nn.DataParallel(net, [0, 1])   # what the reference's init_net builds for gpu_ids=[0,1] (networks.py:115-118)
+    with torch.no_grad():
+        y_dp = dp(*[t.to("cuda:0") for t in inputs]).cpu()
+        y_dp2 = dp(*[t.to("cuda:0") for t in inputs]).cpu()   # replicas of the first call are gone; the original's handle is not
+    assert (y_dp - ys[0]).abs().max().item() == 0 and (y_dp2 - ys[0]).abs().max().item() == 0
