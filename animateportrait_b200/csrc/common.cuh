@@ -53,29 +53,26 @@ struct Act {
   size_t elems() const { return pixels() * C; }
 };
 
-// InstanceNorm statistics of a producer kernel, deterministic and independent of the batch size: every producer warp
-// (or CTA) stores the {sum, sum of squares} of ITS pixels of an image as one partial row -- no two producers share an
-// address, nothing is accumulated with atomics -- and takes a ticket per (image, 32-channel block); whoever draws the
-// last ticket adds the `np` rows of the block up in row order (fp64) and writes the final [B][C][2] doubles.  Which
-// pixels a row covers depends on the image geometry only, never on the batch size, the grid or the timing, so the
-// statistics are bit-identical from run to run and between a batch and its frames run one by one -- like the
-// reference's CPU instance_norm (Module2/models/networks.py:34).  The ticket counters return to zero by themselves.
-struct StatSink {
-  double* stats;    // [B][C][2] final {sum, sumsq}; null: no statistics
-  float2* part;     // [B][np][C] partial rows
-  uint32_t* count;  // [B][C/32] tickets
-  int C, coff;      // channels of the statistics tensor, first channel this producer writes (multiple of 32)
-  int np;           // partial rows per image that make a complete plane
-};
+// InstanceNorm statistics, deterministic and independent of the batch size.  Producers accumulate per-(n,c)
+// {sum, sum of squares} as 64-bit FIXED-POINT integers (STAT_FRAC fractional bits): every leaf -- the float sum of one
+// channel over the 32 pixels one epilogue warp holds, computed in a fixed order -- is rounded to the grid once, and
+// integer addition is associative, so on-chip accumulation and fire-and-forget atomics in ANY order and grouping give
+// bit-identical totals: from run to run, for any batch size, grid or stream timing -- like the reference's CPU
+// instance_norm (Module2/models/networks.py:34), with no tickets, no partial buffers and no reduction tail.
+// Precision: a leaf is off by <= 2^-23; over P leaves of a plane of N pixels the mean and the mean square are off by
+// about sqrt(P) * 2^-23 / N  (<= 4e-10 for every layer of this network) -- against eps = 1e-5 inside the square root
+// that changes rstd by < 1e-5 relative, whatever the scale of the channel.  Range: |sum of squares| < 2^63 / 2^22 =
+// 2.2e12, i.e. an rms of the pre-norm activations below 5,800 at 256x256 (23,000 at 64x64).
+typedef long long stat_t;
+constexpr int STAT_FRAC = 22;
+constexpr double STAT_SCALE = 4194304.0;          // 2^22
+constexpr double STAT_INV_SCALE = 1.0 / 4194304.0;
 
-// Raw (pre-InstanceNorm) conv output: fp32 NHWC, no halo, plus per-(n,c) {sum, sumsq} in double.
+// Raw (pre-InstanceNorm) conv output: fp32 NHWC, no halo, plus per-(n,c) {sum, sumsq} in fixed point.
 struct Raw {
   int B = 0, H = 0, W = 0, C = 0;
   float* p = nullptr;
-  double* stats = nullptr;     // [B][C][2]
-  float2* part = nullptr;      // [B][H*W/32][C] partial rows (upper bound of every producer's np)
-  uint32_t* count = nullptr;   // [B][ceil(C/32)]
-  StatSink sink(int np, int coff = 0) const { return StatSink{stats, part, count, C, coff, np}; }
+  stat_t* stats = nullptr;  // [B][C][2], zeroed at the start of every forward
 };
 
 // Pointers of the tensors a caller hands to one forward.  Kernels that touch caller memory read them from this table
@@ -131,16 +128,16 @@ struct SimtConvP {
   const float* wpk;  // [slab][Cin][Cout] fp32
   float* out;        // raw NHWC
   int out_C, out_coff;
-  double* stats;  // may be null; indexed [(n*stat_C + stat_coff + c)*2]
+  stat_t* stats;  // may be null; indexed [(n*stat_C + stat_coff + c)*2]
   int stat_C, stat_coff;
 };
 
 struct ApplyP {
   const float* raw; int raw_C, raw_coff;
-  const double* stats; int stat_C, stat_coff;  // null -> no normalisation (bias mode)
+  const stat_t* stats; int stat_C, stat_coff;  // null -> no normalisation (bias mode)
   const float* bias;                           // null or [C]
   const float* raw2; int raw2_C, raw2_coff;    // optional second InstanceNorm'ed operand (ResnetBlock2 shortcut)
-  const double* stats2; int stat2_C, stat2_coff;
+  const stat_t* stats2; int stat2_C, stat2_coff;
   const float* res_in;  // optional fp32 residual stream [B,H,W,C] added to the result
   float* res_out;       // optional: result written here as fp32 [B,H,W,C]
   // optional residual read from an ACTIVATION buffer instead (the block input itself: fp32, or bf16 hi + lo)
@@ -156,7 +153,7 @@ struct ApplyP {
 
 struct WarpP {
   const float* raw; int raw_C, raw_coff;       // raw stem/conv output, normalised + ReLU on the fly
-  const double* stats; int stat_C, stat_coff;
+  const stat_t* stats; int stat_C, stat_coff;
   const IoPtrs* io;     // motion [B,256,256,2], flow [B,2,256,256], ifmask [B,1,256,256] of the caller
   int B, S, C, level;   // feature size S, feature channels C, pyramid level 0/1/2
   int src_shared;       // 1: `raw`/`stats` hold ONE image that every frame of the batch warps (clip mode)
@@ -164,7 +161,7 @@ struct WarpP {
 };
 
 struct OutConvP {
-  const float* raw; const double* stats;  // model3.3 raw output [B,256,256,64] + stats (IN+ReLU on the fly)
+  const float* raw; const stat_t* stats;  // model3.3 raw output [B,256,256,64] + stats (IN+ReLU on the fly)
   const float* w;                         // [onc][49][64] fp32
   const float* bias;                      // [onc]
   const IoPtrs* io;                       // io->out: NCHW [B,onc,256,256] of the caller
@@ -174,56 +171,28 @@ struct OutConvP {
 struct ReadP {  // debug tap: Act or Raw(+stats) -> NCHW fp32
   int B, H, W, C;      // logical view
   int fmt; const void* p0; const void* p1; int sC, scoff, spad;
-  const double* stats; int stat_C, stat_coff; int relu;  // stats != null: normalise
+  const stat_t* stats; int stat_C, stat_coff; int relu;  // stats != null: normalise
   float* dst;
 };
 
-// (mean, rstd) of an affine-less InstanceNorm2d from the producer's {sum, sum of squares} (fp64), eps = 1e-5
+// (mean, rstd) of an affine-less InstanceNorm2d from the producer's {sum, sum of squares} (fixed point), eps = 1e-5
 // (nn.InstanceNorm2d default, Module2/models/networks.py:34): biased variance over the H*W plane.
 #ifdef __CUDACC__
-__device__ __forceinline__ void stats_to_affine(const double* st, int n, int stat_C, int stat_coff, int c, double inv_n,
+__device__ __forceinline__ void stats_to_affine(const stat_t* st, int n, int stat_C, int stat_coff, int c, double inv_n,
                                                 float* mean, float* rstd) {
-  const double su = st[((size_t)n * stat_C + stat_coff + c) * 2 + 0];
-  const double sq = st[((size_t)n * stat_C + stat_coff + c) * 2 + 1];
+  const double su = (double)st[((size_t)n * stat_C + stat_coff + c) * 2 + 0] * STAT_INV_SCALE;
+  const double sq = (double)st[((size_t)n * stat_C + stat_coff + c) * 2 + 1] * STAT_INV_SCALE;
   const double m = su * inv_n;
   double var = sq * inv_n - m * m;  // sums are exact enough in double; the reference's own IN is fp32
   if (var < 0.0) var = 0.0;
   *mean = (float)m;
   *rstd = 1.0f / sqrtf((float)var + 1e-5f);
 }
-#endif
-
-#ifdef __CUDACC__
-// One warp; lane L holds {sum, sumsq} over the warp's pixels of channel c0 + L: store partial row `row` of image n.
-__device__ __forceinline__ void stat_put(const StatSink& s, int n, int row, int c0, int lane, float cs, float cq) {
-  s.part[((size_t)n * s.np + row) * s.C + s.coff + c0 + lane] = make_float2(cs, cq);
-}
-// One warp, after it has stored its rows of `nblk` consecutive 32-channel blocks starting at channel c0 of image n:
-// one ticket per block; the last arriver of a block reduces it in row order.
-__device__ __forceinline__ void stat_arrive(const StatSink& s, int n, int c0, int nblk, int lane) {
-  __threadfence();
-  __syncwarp();
-  uint32_t* cnt = s.count + (size_t)n * (s.C >> 5) + ((s.coff + c0) >> 5);
-  uint32_t t = 0;
-  if (lane < nblk) t = atomicAdd(cnt + lane, 1u);
-  uint32_t last = __ballot_sync(0xffffffffu, lane < nblk && t == (uint32_t)(s.np - 1));
-  while (last) {
-    const int b = __ffs(last) - 1;
-    last &= last - 1;
-    __threadfence();
-    const float2* src = s.part + (size_t)n * s.np * s.C + s.coff + c0 + 32 * b + lane;
-    double su = 0.0, sq = 0.0;
-#pragma unroll 8
-    for (int r = 0; r < s.np; ++r) {
-      const float2 v = __ldcg(src + (size_t)r * s.C);
-      su += (double)v.x;
-      sq += (double)v.y;
-    }
-    double* dst = s.stats + ((size_t)n * s.C + s.coff + c0 + 32 * b + lane) * 2;
-    dst[0] = su;
-    dst[1] = sq;
-    if (lane == 0) cnt[b] = 0;  // the counters are back at zero when the kernel ends
-  }
+// leaf of the statistics: a float partial sum on the fixed-point grid
+__device__ __forceinline__ stat_t stat_fix(float v) { return __double2ll_rn((double)v * STAT_SCALE); }
+// fire-and-forget 64-bit integer atomic (RED.ADD.64): order-independent
+__device__ __forceinline__ void stat_add(stat_t* dst, stat_t v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(v));
 }
 #endif
 
@@ -234,6 +203,7 @@ int launch_set_io(IoPtrs* dst, const IoPtrs& v, cudaStream_t st);  // refreshes 
 int launch_warp(const WarpP& p, cudaStream_t st);
 int launch_out_conv(const OutConvP& p, cudaStream_t st);
 int launch_read(const ReadP& p, cudaStream_t st);
+int launch_stats_to_double(const stat_t* src, double* dst, size_t n, cudaStream_t st);  // debug: fixed point -> double
 // weight packing: src torch layout -> [slab][Cin][simt_C] fp32 at column simt_coff (simt) and/or
 // [slab][Cout][Cin] bf16 hi,lo (umma)
 int launch_pack_weights(const float* src, int Cout, int Cin, int k, int transposed, float* dst_simt, int simt_C,
@@ -249,15 +219,10 @@ int launch_nchw_to_act(const float* src, const Act& dst, cudaStream_t st);  // d
 
 // ---- tcgen05 conv ----
 struct UmmaConv;  // opaque launch record (tensor maps + params), see conv_umma.cu
-// `sink`: where the InstanceNorm statistics of the output go (sink.stats null: none).  Partial row of (tile t of the
-// image, epilogue warp q) = (4 t + q) * slot_mul + slot_add: a layer computed by several convs over the same virtual
-// grid (the phases of a transposed conv) gives each conv its own slot_add < slot_mul; sink.np must be
-// 4 * tiles per image * slot_mul.
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff,
                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int nprod,
-                     float* out_raw, int out_C, int out_coff, const StatSink& sink, int slot_mul = 1, int slot_add = 0,
+                     float* out_raw, int out_C, int out_coff, stat_t* stats, int stat_C, int stat_coff,
                      const PhasePack* pk = nullptr);
-int umma_conv_stat_rows(const ConvGeom& g);  // 4 * tiles per image of this geometry
 bool umma_pairs_available();  // CTA-pair kernels enabled and launchable on this device
 void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
@@ -273,7 +238,6 @@ int tmap_encode_out(CUtensorMap* m, float* out, int B, int Hout, int Wout, int C
 size_t stem_umma_weight_bytes();
 int launch_pack_stem_umma(const float* src, int cout_s, int coff, uint8_t* img, cudaStream_t st);
 int launch_stem_umma(const IoPtrs* io, const uint8_t* wimg, const Raw& out, int B, int nprod, cudaStream_t st);
-constexpr int STEM_STAT_ROWS = 512;  // 128 groups of 4 tiles x 4 epilogue warps per image
 
 // ---- tcgen05 output stage (conv_out.cu): IN+ReLU -> RefPad3 -> Conv7x7 64->onc -> bias -> tanh ----
 size_t out_umma_weight_bytes(int onc);

@@ -40,7 +40,7 @@ constexpr size_t O_SMEM = 1024 + O_MAX_ONC * O_WIMG + 2 * O_ASLOT + O_TBYTES + 5
 
 struct OutUmmaP {
   const float* raw;       // [B,256,256,64] raw output of model3.3 (pre-InstanceNorm)
-  const double* stats;    // [B][64][2]
+  const stat_t* stats;    // [B][64][2] fixed point
   const uint8_t* wimg;    // onc x O_WIMG pre-swizzled weight images
   const float* bias;      // [onc]
   const IoPtrs* io;       // io->out: [B,onc,256,256] of the caller (may be peer memory: plain stores)

@@ -9,7 +9,7 @@
 //    preceding InstanceNorm+ReLU applied while the input tile is staged in shared memory.
 //
 // Every conv that feeds an affine-less InstanceNorm drops its bias (it cancels exactly; SURVEY.md §8
-// a14) and emits per-(n,c) sum / sum-of-squares in double via one atomic per channel per CTA.
+// a14) and emits per-(n,c) sum / sum-of-squares (fixed point, common.cuh) via one atomic per channel per CTA.
 #include "common.cuh"
 
 namespace ap {
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvP p) {
         float t = 0.f;
 #pragma unroll
         for (int r = 0; r < 16; ++r) t += red[which][r][c];
-        atomicAdd(p.stats + ((size_t)(img * p.stat_C + p.stat_coff + n0 + c)) * 2 + which, (double)t);
+        stat_add(p.stats + ((size_t)(img * p.stat_C + p.stat_coff + n0 + c)) * 2 + which, stat_fix(t));
       }
     }
   }
@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const OutConvP p) {
   for (int i = tid; i < ONC * 49 * 64; i += 128) wsm[i] = p.w[i];
   if (tid < 64) {
     const double inv = 1.0 / (double)(S * S);
-    const double su = p.stats[((size_t)n * 64 + tid) * 2 + 0];
-    const double sq = p.stats[((size_t)n * 64 + tid) * 2 + 1];
+    const double su = (double)p.stats[((size_t)n * 64 + tid) * 2 + 0] * STAT_INV_SCALE;
+    const double sq = (double)p.stats[((size_t)n * 64 + tid) * 2 + 1] * STAT_INV_SCALE;
     const double m = su * inv;
     double var = sq * inv - m * m;
     if (var < 0.0) var = 0.0;

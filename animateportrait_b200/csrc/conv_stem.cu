@@ -19,8 +19,8 @@
 //
 // Warp roles (416 threads): warp 0 = TMEM allocator, weight loader, MMA issuer; warps 1-8 = A builders (two groups
 // splitting the K range); warps 9-12 = epilogue (tcgen05.ld -> raw fp32 NHWC store + per-channel sum / sum of squares for the
-// following InstanceNorm, accumulated in registers across a GROUP of 4 consecutive tiles = two full image rows; CTAs own
-// whole groups, so the partial rows are the same for any batch size -- then stored through StatSink, common.cuh).
+// following InstanceNorm, accumulated in registers -- as fixed-point integers, common.cuh: stat_t -- across the CTA's
+// tiles of one image).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -48,7 +48,7 @@ struct StemP {
   const IoPtrs* io;      // io->input: [B,3,256,256] NCHW fp32 of the caller
   const uint8_t* wimg;   // ST_WBYTES: [plane][chunk][160 rows][64 k] bf16, 128B-swizzled smem image
   float* out;            // raw NHWC [B,256,256,160]
-  StatSink sink;         // [B][160][2]; partial row = 4 * (group of the image) + epilogue warp, np = STEM_STAT_ROWS
+  stat_t* stats;         // [B][160][2] fixed point
   int tiles;             // B * 512 (tile = 2 rows x 64 px)
   int dbg;               // AP_STEM_DBG timing probe: 1 = no output stores, 2 = no statistics, 4 = builders skip the A build
 };
@@ -105,11 +105,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sgen + ST_WBYTES + ST_RING + ST_EPI + ST_PATCH * 4 + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous range of tile groups of this CTA (4 tiles per group, 128 groups per image)
+  // contiguous tile range of this CTA
   const int G = gridDim.x;
-  const int ngroups = p.tiles >> 2;
-  const int t_begin = 4 * (int)(((long long)blockIdx.x * ngroups) / G);
-  const int t_end = 4 * (int)(((long long)(blockIdx.x + 1) * ngroups) / G);
+  const int t_begin = (int)(((long long)blockIdx.x * p.tiles) / G);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * p.tiles) / G);
   const int ntiles = t_end - t_begin;
 
   if (warp == 0) {
@@ -255,9 +254,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
     uint8_t* slab_gen = epi_gen + q * 8192;
     const uint32_t slab_s = epi_s + q * 8192;
     uint32_t blk = 0;
-    float ssum[5], ssq[5];
+    stat_t ssum[5], ssq[5];  // fixed point: any grouping of the tiles gives the same totals
 #pragma unroll
-    for (int g = 0; g < 5; ++g) { ssum[g] = 0.f; ssq[g] = 0.f; }
+    for (int g = 0; g < 5; ++g) { ssum[g] = 0; ssq[g] = 0; }
     for (int it = 0; it < ntiles; ++it) {
       const int t = t_begin + it;
       const int img = t >> 9, rem = t & 511;
@@ -274,21 +273,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_umma_kernel(const __grid_c
         if (p.dbg & 2) continue;
         float cs, cq;
         slab_colsums(slab_gen + sl, lane, &cs, &cq);
-        ssum[g] += cs;
-        ssq[g] += cq;
+        ssum[g] += stat_fix(cs);
+        ssq[g] += stat_fix(cq);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 64 + 8 * acc);
-      if ((t & 3) == 3 && !(p.dbg & 2)) {  // end of a group of 4 tiles
-        const int row = ((rem >> 2) * 4 + q);
+      const bool flush = (it == ntiles - 1) || (((t + 1) >> 9) != img);
+      if (flush) {
 #pragma unroll
         for (int g = 0; g < 5; ++g) {
-          stat_put(p.sink, img, row, g * 32, lane, ssum[g], ssq[g]);
-          ssum[g] = 0.f;
-          ssq[g] = 0.f;
+          stat_t* st = p.stats + ((size_t)img * ST_N + g * 32 + lane) * 2;
+          stat_add(st, ssum[g]);
+          stat_add(st + 1, ssq[g]);
+          ssum[g] = 0;
+          ssq[g] = 0;
         }
-        stat_arrive(p.sink, img, 0, 5, lane);
       }
     }
     if (lane == 0) bulk_wait<0>();
@@ -347,14 +347,13 @@ int launch_stem_umma(const IoPtrs* io, const uint8_t* wimg, const Raw& out, int 
   AP_TRY(umma_init());
   StemP p{};
   AP_TRY(tmap_encode_out(&p.tmO, out.p, B, 256, 256, ST_N, 1, 0, 0));
-  p.io = io; p.wimg = wimg; p.out = out.p; p.sink = out.sink(STEM_STAT_ROWS); p.tiles = B * 512;
+  p.io = io; p.wimg = wimg; p.out = out.p; p.stats = out.stats; p.tiles = B * 512;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("AP_STEM_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
   }
-  const int groups = p.tiles / 4;
-  const int grid = groups < g_stem_sms ? groups : g_stem_sms;
+  const int grid = p.tiles < g_stem_sms ? p.tiles : g_stem_sms;
   if (nprod == 3)
     stem_umma_kernel<3><<<grid, ST_THREADS, ST_SMEM, st>>>(p);
   else

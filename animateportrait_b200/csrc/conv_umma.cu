@@ -20,8 +20,8 @@
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 //   warps 2..5 = epilogue: tcgen05.ld 32 columns at a time, stage them in a swizzled 4 KB slab and
 //   TMA-store the {32 ch, 32 px} box (coalesced, asynchronous), and read the per-channel sum /
-//   sum-of-squares of the block back from the slab for the following InstanceNorm: one partial row per
-//   (tile, warp), reduced in a fixed order by the last arriver (StatSink, common.cuh) -- no atomics on data.
+//   sum-of-squares of the block back from the slab for the following InstanceNorm, as fixed-point integers
+//   (common.cuh: stat_t): accumulated on chip / with fire-and-forget atomics in any order, bit-identically.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
@@ -52,8 +52,8 @@ struct alignas(64) UmmaParams {
   int kchunks, last_ksteps, cin_off;
   int tiles_x, tiles_y, TW, TH, stride;
   int out_coff;
-  StatSink sink;            // InstanceNorm statistics of the output (sink.stats null: none)
-  int slot_mul, slot_add;   // partial row of (tile t of the image, epilogue warp q) = (4 t + q) * slot_mul + slot_add
+  stat_t* stats;            // InstanceNorm statistics of the output, fixed point (null: none)
+  int stat_C, stat_coff;
   // item list in units of tile GROUPS (CG consecutive 128-pixel tiles, one per CTA of the pair):
   // n_full whole groups with bn = Cout, then (groups - n_full) * split N-parts
   int n_full, split, n_items;
@@ -88,24 +88,45 @@ struct UmmaCfg {
   static constexpr int EPI_BYTES = EpiCfg<BN>::BYTES;
   static constexpr int STAGES_RAW = (226 * 1024 - 2 * 4 * 4096 - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 + (CG == 1 && BN <= 128 ? 8192 : 0);
 };
 
 struct Item {
   int img, ty, tx, n0, bn;
 };
 
-// Local item `li` of execution unit `unit` (CTA, or CTA pair) -> global item index, or -1 when the unit is done:
-// neighbouring units work on neighbouring tiles.
-__device__ __forceinline__ int item_at(const UmmaParams& p, int li, int unit, int nunits) {
-  const int it = unit + li * nunits;
+// Local item `li` of execution unit `unit` (CTA, or CTA pair) -> global item index, or -1 when the unit is done.
+// STRIDED: item = unit + li * nunits (neighbouring CTAs work on neighbouring tiles).  CONTIGUOUS (used where the
+// InstanceNorm statistics are accumulated on chip): the whole-wave part of the item list is dealt in runs, unit u
+// owning [u*K, (u+1)*K), so that consecutive items of a unit lie in the same image; tail items stay strided.
+template <bool CONTIGUOUS>
+__device__ __forceinline__ int item_at(const UmmaParams& p, int li, int unit, int nunits, int K) {
+  if (!CONTIGUOUS) {
+    const int it = unit + li * nunits;
+    return it < p.n_items ? it : -1;
+  }
+  if (li < K) return unit * K + li;
+  const int it = p.n_full + (li - K) * nunits + unit;
   return it < p.n_items ? it : -1;
 }
 
-// Phase-packed transposed convs: the column blocks of one item that belong to different output phases fold onto the
-// same channel; each epilogue warp folds them in shared memory (column order) before it stores its partial row.
+// Per-warp accumulation of the InstanceNorm statistics in shared memory across the items of one image: one
+// atomic per (channel, warp, image run) instead of one per (channel, warp, tile).  Atomics on one address
+// serialise in L2; layers with few channels and thousands of tiles were bound by exactly that
+// (profiles/r01_stat_atomics.md: 128->64 transposed conv 307 -> 138 us without statistics).  The accumulators are
+// fixed-point integers like the totals: how the items are grouped into runs does not change a bit of the result.
 constexpr int STAT_ACC_COLS = 128;
-constexpr int STAT_ACC_BYTES = 4 * 2 * STAT_ACC_COLS * 4;  // 4 epilogue warps x {sum, sumsq} x 128 channels x fp32
+constexpr int STAT_ACC_BYTES = 4 * 2 * STAT_ACC_COLS * 8;  // 4 epilogue warps x {sum, sumsq} x 128 channels x int64
+
+__device__ __forceinline__ void stat_flush(stat_t* sacc, stat_t* stats, int stat_C, int stat_coff, int img, int ncols, int lane) {
+  for (int c = lane; c < ncols; c += 32) {
+    stat_t* dst = stats + ((size_t)img * stat_C + stat_coff + c) * 2;
+    stat_add(dst, sacc[c]);
+    stat_add(dst + 1, sacc[STAT_ACC_COLS + c]);
+    sacc[c] = 0;
+    sacc[STAT_ACC_COLS + c] = 0;
+  }
+}
 
 // ---- single-CTA kernel (cta_group::1): one CTA per 128-pixel tile; used for the N <= 128 layers ----
 __device__ __forceinline__ Item decode_item1(const UmmaParams& p, int item, int BN) {
@@ -144,6 +165,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = p.ntaps * p.kchunks;
+  constexpr bool ACC = BN <= STAT_ACC_COLS;  // statistics accumulated on chip, contiguous item runs
+  const int Krun = ACC ? p.n_full / (int)gridDim.x : 0;
+  stat_t* sacc_all = reinterpret_cast<stat_t*>(epi_gen + EPI_BYTES + 256);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
@@ -179,7 +203,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     if (lane == 0) {
       uint32_t cnt = 0;
       for (int li = 0;; ++li) {
-        const int item = item_at(p, li, blockIdx.x, gridDim.x);
+        const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
         if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
@@ -214,7 +238,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     if (lane == 0) {
       uint32_t cnt = 0, local = 0;
       for (int li = 0;; ++li, ++local) {
-        const int item = item_at(p, li, blockIdx.x, gridDim.x);
+        const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
         if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
@@ -267,32 +291,50 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
     const uint32_t slab_s = epi_s + q * (EPI_SLABS * 4096);
     const uint64_t opol = (p.l2_hints & 1) ? l2_policy_evict_last() : 0;  // raw output is re-read by the next kernel
     uint32_t local = 0, blk = 0;
+    stat_t* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
+    int simg = -1;
+    if (ACC) {
+      for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0;
+      __syncwarp();
+    }
     for (int li = 0;; ++li, ++local) {
-      const int item = item_at(p, li, blockIdx.x, gridDim.x);
+      const int item = item_at<ACC>(p, li, blockIdx.x, gridDim.x, Krun);
       if (item < 0) break;
       const Item w = decode_item1(p, item, BN);
+      const bool acc_item = ACC && w.bn == BN;  // N-split tail items use direct atomics
+      if (ACC && simg >= 0 && (w.img != simg || !acc_item)) {
+        stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, BN, lane);
+        simg = -1;
+      }
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
       const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
-      const int srow = ((w.ty * p.tiles_x + w.tx) * 4 + q) * p.slot_mul + p.slot_add;
+      stat_t* strow = p.stats ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + w.n0 + lane) * 2 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)row0 << 16) + acc * 256u + (uint32_t)c0, v);
         const uint32_t sl = (blk % EPI_SLABS) * 4096;
         epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[0], p.out_coff + w.n0 + c0, ox, oy, w.img, opol);
-        if (p.sink.stats != nullptr) {
+        if (strow != nullptr) {
           float cs, cq;
           slab_colsums(slab_gen + sl, lane, &cs, &cq);
-          stat_put(p.sink, w.img, srow, w.n0 + c0, lane, cs, cq);
+          if (acc_item) {
+            sacc[c0 + lane] += stat_fix(cs);
+            sacc[STAT_ACC_COLS + c0 + lane] += stat_fix(cq);
+            simg = w.img;
+          } else {
+            stat_add(strow + (size_t)c0 * 2, stat_fix(cs));
+            stat_add(strow + (size_t)c0 * 2 + 1, stat_fix(cq));
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 144 + 8 * acc);
-      if (p.sink.stats != nullptr) stat_arrive(p.sink, w.img, w.n0, w.bn >> 5, lane);
     }
+    if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, BN, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
   }
   tc_fence_before();
@@ -327,8 +369,8 @@ __device__ __forceinline__ Item decode_item(const UmmaParams& p, int item, int B
 
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) runs tcgen05.mma.cta_group::2
 // with M = 256; each CTA stages its own A tile and half of the weight tile, the leader (cluster rank 0) issues.
-// PACKED (phase-packed transposed convs): the phases of an item fold onto the same channels before the statistics
-// row is stored; one staging slab.
+// PACKED (phase-packed transposed convs): statistics accumulated on chip over contiguous item runs (the phases fold onto
+// the same channels), one staging slab.
 template <int BN, int NPROD, int CG, bool PACKED>
 __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   using Cfg = UmmaCfg<BN, NPROD, CG>;
@@ -341,6 +383,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   uint8_t* epi_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
   constexpr int EPI_SLABS = PACKED ? 1 : EpiCfg<BN>::SLABS;
   constexpr int EPI_BYTES = 4 * EPI_SLABS * 4096;
+  constexpr bool ACC = PACKED;
   const uint32_t bars = epi_s + EPI_BYTES;
   // barriers: full[s] +8s, empty[s] +64+8s, tfull[a] +128+8a, tempty[a] +144+8a, tmem ptr +160
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + EPI_BYTES + 160);
@@ -350,7 +393,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // pair (or CTA) index
   const int nunits = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  float* sacc_all = reinterpret_cast<float*>(epi_gen + EPI_BYTES + 256);
+  const int Krun = ACC ? p.n_full / nunits : 0;
+  stat_t* sacc_all = reinterpret_cast<stat_t*>(epi_gen + EPI_BYTES + 256);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[0]) : "memory");
@@ -395,7 +439,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       const uint32_t full0 = (CG == 2) ? mapa_rank(bars, 0) : bars;  // full barriers live in the leader
       uint32_t cnt = 0;
       for (int li = 0;; ++li) {
-        const int item = item_at(p, li, unit, nunits);
+        const int item = item_at<ACC>(p, li, unit, nunits, Krun);
         if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, rank);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
@@ -442,7 +486,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     if (lane == 0 && rank == 0) {
       uint32_t cnt = 0, local = 0;
       for (int li = 0;; ++li, ++local) {
-        const int item = item_at(p, li, unit, nunits);
+        const int item = item_at<ACC>(p, li, unit, nunits, Krun);
         if (item < 0) break;
         const Item w = decode_item(p, item, BN, CG, 0);
         // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
@@ -509,21 +553,26 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     const uint32_t tempty0 = (CG == 2) ? mapa_rank(bars + 144, 0) : bars + 144;
     const uint64_t opol = (p.l2_hints & 1) ? l2_policy_evict_last() : 0;  // raw output is re-read by the next kernel
     uint32_t local = 0, blk = 0;
-    float* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
-    if (PACKED) {
-      for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0.f;
+    stat_t* sacc = sacc_all + q * (2 * STAT_ACC_COLS);
+    int simg = -1;
+    if (ACC) {
+      for (int c = lane; c < 2 * STAT_ACC_COLS; c += 32) sacc[c] = 0;
       __syncwarp();
     }
     for (int li = 0;; ++li, ++local) {
-      const int item = item_at(p, li, unit, nunits);
+      const int item = item_at<ACC>(p, li, unit, nunits, Krun);
       if (item < 0) break;
       const Item w = decode_item(p, item, BN, CG, rank);
+      const bool acc_item = ACC && p.phase_cols > 0 && p.phase_cols <= STAT_ACC_COLS;
+      if (ACC && simg >= 0 && w.img != simg) {
+        stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
+        simg = -1;
+      }
       const uint32_t acc = local & 1u;
       mbar_wait(bars + 128 + 8 * acc, (local >> 1) & 1u);
       tc_fence_after();
       const int ox = w.tx * p.TW + xx0, oy = w.ty * p.TH + yy;
-      const int srow = ((w.ty * p.tiles_x + w.tx) * 4 + q) * p.slot_mul + p.slot_add;
-      const bool want_stats = p.sink.stats != nullptr && !AP_DBG(p.dbg & 4);
+      stat_t* strow = (p.stats && !AP_DBG(p.dbg & 4)) ? p.stats + ((size_t)w.img * p.stat_C + p.stat_coff + lane) * 2 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < w.bn; c0 += 32, ++blk) {
         float v[32];
@@ -534,14 +583,16 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         if (p.phase_cols) { phs = ch / p.phase_cols; ch -= phs * p.phase_cols; }
         if (!AP_DBG(p.dbg & 2))
           epi_store_block<EPI_SLABS - 1>(v, slab_gen + sl, slab_s + sl, lane, &p.tmO[phs], p.out_coff + ch, ox, oy, w.img, opol);
-        if (want_stats) {
+        if (strow != nullptr) {
           float cs, cq;
           slab_colsums(slab_gen + sl, lane, &cs, &cq);
-          if (PACKED) {  // the phases of a packed transposed conv fold onto the same channel, in column order
-            sacc[ch + lane] += cs;
-            sacc[STAT_ACC_COLS + ch + lane] += cq;
+          if (acc_item) {  // the phases of a packed transposed conv fold onto the same channel
+            sacc[ch + lane] += stat_fix(cs);
+            sacc[STAT_ACC_COLS + ch + lane] += stat_fix(cq);
+            simg = w.img;
           } else {
-            stat_put(p.sink, w.img, srow, ch, lane, cs, cq);
+            stat_add(strow + (size_t)ch * 2, stat_fix(cs));
+            stat_add(strow + (size_t)ch * 2 + 1, stat_fix(cq));
           }
         }
       }
@@ -551,20 +602,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * acc);
         else mbar_arrive(bars + 144 + 8 * acc);
       }
-      if (want_stats) {
-        if (PACKED) {  // packed items are never split along N: all phases of the tile are in this item
-          const int nblk = p.phase_cols >> 5;
-          for (int b = 0; b < nblk; ++b) {
-            stat_put(p.sink, w.img, srow, 32 * b, lane, sacc[32 * b + lane], sacc[STAT_ACC_COLS + 32 * b + lane]);
-            sacc[32 * b + lane] = 0.f;
-            sacc[STAT_ACC_COLS + 32 * b + lane] = 0.f;
-          }
-          stat_arrive(p.sink, w.img, 0, nblk, lane);
-        } else {
-          stat_arrive(p.sink, w.img, w.n0, w.bn >> 5, lane);
-        }
-      }
     }
+    if (ACC && simg >= 0) stat_flush(sacc, p.stats, p.stat_C, p.stat_coff, simg, p.phase_cols, lane);
     if (lane == 0) bulk_wait<0>();  // all output boxes have landed before the CTA exits
     __syncwarp();
   }
@@ -716,15 +755,9 @@ static int conv_tiling(const ConvGeom& g, int* TW, int* TH) {
   return AP_OK;
 }
 
-int umma_conv_stat_rows(const ConvGeom& g) {
-  int TW = 0, TH = 0;
-  if (conv_tiling(g, &TW, &TH) != AP_OK) return 0;
-  return (g.Wv / TW) * (g.Hv / TH) * 4;
-}
-
 int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
-                     const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, const StatSink& sink,
-                     int slot_mul, int slot_add, const PhasePack* pk) {
+                     const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, stat_t* stats,
+                     int stat_C, int stat_coff, const PhasePack* pk) {
   AP_TRY(umma_init());
   AP_REQUIRE(in.fmt == FMT_BF16X2 || in.fmt == FMT_BF16, AP_ERR_INVALID, "umma conv needs bf16 activations");
   AP_REQUIRE(nprod == 1 || (nprod == 3 && in.fmt == FMT_BF16X2 && w_lo), AP_ERR_INVALID, "umma conv: nprod/format");
@@ -798,21 +831,14 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   p.tiles_x = g.Wv / TW; p.tiles_y = g.Hv / TH;
   p.stride = g.stride;
   p.out_coff = out_coff;
-  p.sink = sink;
-  if (g_dbg & 8) p.sink.stats = nullptr;  // AP_UMMA_DBG bit 3 (timing probe only): no InstanceNorm statistics at all
-  p.slot_mul = slot_mul; p.slot_add = slot_add;
-  if (sink.stats != nullptr) {
-    AP_REQUIRE(sink.part && sink.count && sink.C % 32 == 0 && sink.coff % 32 == 0 && slot_add < slot_mul &&
-                   sink.np == (g.Wv / TW) * (g.Hv / TH) * 4 * slot_mul,
-               AP_ERR_INVALID, "umma conv: statistics sink (C=%d coff=%d np=%d, %d tiles x %d)", sink.C, sink.coff, sink.np,
-               (g.Wv / TW) * (g.Hv / TH), slot_mul);
-  }
+  p.stats = (g_dbg & 8) ? nullptr : stats;  // AP_UMMA_DBG bit 3 (timing probe only): no InstanceNorm statistics at all
+  p.stat_C = stat_C; p.stat_coff = stat_coff;
   // item list: whole waves of full tile groups, the remainder split along N so the tail fills the machine
   const int groups = ntiles / c->cg;
   const int G = c->cg == 2 ? pairs : (g_sms > 0 ? g_sms : 148);  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
   const int rem = groups % G;
   int split = 1;
-  if (rem > 0 && !pk) {  // packed items stay whole: their phases fold onto the same channels inside one epilogue warp
+  if (rem > 0) {
     while (split < 4 && rem * split * 2 <= G && wrows / (split * 2) >= 64) split *= 2;
   }
   p.split = split;

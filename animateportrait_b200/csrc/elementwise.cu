@@ -482,6 +482,17 @@ __global__ void read_kernel(const ReadP p) {
   }
 }
 
+__global__ void stats_to_double_kernel(const stat_t* __restrict__ src, double* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (double)src[i] * STAT_INV_SCALE;
+}
+
+int launch_stats_to_double(const stat_t* src, double* dst, size_t n, cudaStream_t st) {
+  stats_to_double_kernel<<<64, 256, 0, st>>>(src, dst, n);
+  AP_CUDA(cudaGetLastError());
+  return AP_OK;
+}
+
 int launch_read(const ReadP& p, cudaStream_t st) {
   read_kernel<<<1184, 256, 0, st>>>(p);
   AP_CUDA(cudaGetLastError());

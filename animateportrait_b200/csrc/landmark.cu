@@ -22,11 +22,9 @@ template <int CIN, int COUT>
 struct LandP {
   const IoPtrs* io;   // CIN == 1: io->land1 [B1,1,256,256], io->land2 [B2,1,256,256] of the caller
   const float* in0;   // CIN > 1: raw NHWC [B1+B2,Hin,Win,CIN]
-  const double* in_stats;  // [B1+B2][CIN][2] (CIN > 1)
+  const stat_t* in_stats;  // [B1+B2][CIN][2] (CIN > 1), fixed point
   float* out;         // raw NHWC [B1+B2,Hout,Wout,COUT]
-  double* out_stats;  // [B1+B2][COUT][2]
-  float* part;        // [B1+B2][CTAs per image][2*COUT]: per-CTA {sums, sums of squares}, reduced in CTA order by the
-  uint32_t* count;    // [B1+B2] tickets                   last CTA of the image (deterministic, see StatSink)
+  stat_t* out_stats;  // [B1+B2][COUT][2], fixed point
   int B, Hin, Hout;   // B = B1, the number of land1 maps (the batch size, or 1 in clip mode: one source landmark map)
   float w[9 * CIN * COUT];
 };
@@ -35,7 +33,6 @@ template <int CIN, int COUT, int STRIDE>
 __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ LandP<CIN, COUT> p) {
   __shared__ float s_mean[CIN], s_rstd[CIN];
   __shared__ float s_red[8][2 * COUT];
-  __shared__ uint32_t s_ticket;
   const int tid = threadIdx.x;
   const int HWo = p.Hout * p.Hout;
   const int gpix = blockIdx.x * 256 + tid;  // Hout*Hout is a multiple of 256: one image per CTA
@@ -44,8 +41,8 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
   const int oy = pix / p.Hout, ox = pix - oy * p.Hout;
   if (CIN > 1 && tid < CIN) {
     const double inv = 1.0 / (double)(p.Hin * p.Hin);
-    const double su = p.in_stats[((size_t)n * CIN + tid) * 2 + 0];
-    const double sq = p.in_stats[((size_t)n * CIN + tid) * 2 + 1];
+    const double su = (double)p.in_stats[((size_t)n * CIN + tid) * 2 + 0] * STAT_INV_SCALE;
+    const double sq = (double)p.in_stats[((size_t)n * CIN + tid) * 2 + 1] * STAT_INV_SCALE;
     const double m = su * inv;
     double var = sq * inv - m * m;
     if (var < 0.0) var = 0.0;
@@ -93,8 +90,8 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
 #pragma unroll
   for (int o4 = 0; o4 < COUT / 4; ++o4) dst[o4] = make_float4(acc[o4 * 4], acc[o4 * 4 + 1], acc[o4 * 4 + 2], acc[o4 * 4 + 3]);
 
-  // per-channel sum / sum of squares in a fixed order: warp shuffle tree, the 8 warps of the CTA in warp order, the
-  // CTAs of the image in CTA order (by whichever CTA finishes last)
+  // per-channel sum / sum of squares of the CTA's 256 pixels in a fixed order (warp shuffle tree, then the 8 warps in
+  // warp order), rounded to the fixed-point grid once and added to the totals with an order-independent integer atomic
 #pragma unroll
   for (int o = 0; o < COUT; ++o) {
     float s = acc[o], q = acc[o] * acc[o];
@@ -109,29 +106,12 @@ __global__ void __launch_bounds__(256) land_conv_kernel(const __grid_constant__ 
     }
   }
   __syncthreads();
-  const int ctas = HWo / 256;
-  const int cta = blockIdx.x - n * ctas;
   if (tid < 2 * COUT) {
+    const int which = tid / COUT, c = tid - which * COUT;
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s_red[w][tid];
-    p.part[((size_t)n * ctas + cta) * (2 * COUT) + tid] = t;
-    __threadfence();
-  }
-  __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(p.count + n, 1u);
-  __syncthreads();
-  if (s_ticket == (uint32_t)(ctas - 1)) {
-    __threadfence();
-    if (tid < 2 * COUT) {
-      const int which = tid / COUT, c = tid - which * COUT;
-      const float* src = p.part + (size_t)n * ctas * (2 * COUT) + tid;
-      double t = 0.0;
-#pragma unroll 8
-      for (int r = 0; r < ctas; ++r) t += (double)__ldcg(src + (size_t)r * (2 * COUT));
-      p.out_stats[((size_t)n * COUT + c) * 2 + which] = t;
-    }
-    if (tid == 0) p.count[n] = 0;
+    stat_add(p.out_stats + ((size_t)n * COUT + c) * 2 + which, stat_fix(t));
   }
 }
 
@@ -147,19 +127,19 @@ int launch_landmark_branch(const IoPtrs* io, const float* w0, const float* w1, c
     cudaFuncSetAttribute(land_conv_kernel<16, 16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   {
-    LandP<1, 8> a{io, nullptr, nullptr, r0.p, r0.stats, reinterpret_cast<float*>(r0.part), r0.count, B1, 256, 256, {}};
+    LandP<1, 8> a{io, nullptr, nullptr, r0.p, r0.stats, B1, 256, 256, {}};
     memcpy(a.w, w0, sizeof(a.w));
     land_conv_kernel<1, 8, 1><<<NB * 65536 / 256, 256, 0, st>>>(a);
     AP_CUDA(cudaGetLastError());
   }
   {
-    LandP<8, 16> b{nullptr, r0.p, r0.stats, r1.p, r1.stats, reinterpret_cast<float*>(r1.part), r1.count, B1, 256, 128, {}};
+    LandP<8, 16> b{nullptr, r0.p, r0.stats, r1.p, r1.stats, B1, 256, 128, {}};
     memcpy(b.w, w1, sizeof(b.w));
     land_conv_kernel<8, 16, 2><<<NB * 16384 / 256, 256, 0, st>>>(b);
     AP_CUDA(cudaGetLastError());
   }
   {
-    LandP<16, 16> c{nullptr, r1.p, r1.stats, r2.p, r2.stats, reinterpret_cast<float*>(r2.part), r2.count, B1, 128, 64, {}};
+    LandP<16, 16> c{nullptr, r1.p, r1.stats, r2.p, r2.stats, B1, 128, 64, {}};
     memcpy(c.w, w2, sizeof(c.w));
     land_conv_kernel<16, 16, 2><<<NB * 4096 / 256, 256, 0, st>>>(c);
     AP_CUDA(cudaGetLastError());

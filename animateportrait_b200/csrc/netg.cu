@@ -81,7 +81,7 @@ struct LayerW {
 struct TapRec {
   int B, H, W, C;
   int fmt; const void* p0; const void* p1; int sC, scoff, spad;
-  const double* stats; int stat_C, stat_coff; int relu;
+  const stat_t* stats; int stat_C, stat_coff; int relu;
 };
 
 constexpr size_t AP_MAX_PLANS = 6;
@@ -94,12 +94,8 @@ struct Plan {
   uint64_t last_use = 0;  // plan cache is LRU-bounded (AP_MAX_PLANS): ragged tail batches of clips must not pile up arenas
   char* arena = nullptr;
   size_t arena_bytes = 0;
-  // InstanceNorm statistics (final doubles) and the ticket counters of their producers.  The tensor-core modes never
-  // zero it after plan creation (producers overwrite the statistics and return the counters to zero themselves); a
-  // forward that failed half-way marks it dirty.  The CUDA-core validation mode accumulates with atomics: zeroed per call.
-  char* sarena = nullptr;
+  char* sarena = nullptr;  // InstanceNorm statistics (fixed-point accumulators), zeroed at the start of every forward
   size_t sarena_bytes = 0;
-  bool sarena_dirty = false;
   bool keep_all = false;   // debug taps: every intermediate keeps its own buffer (no reuse of dead buffers)
   IoPtrs* d_io = nullptr;  // pointer table of the caller's tensors, read by the kernels that touch caller memory
   // the launch sequence of a plan does not depend on the call (pointer table): captured once, replayed as a CUDA graph
@@ -288,12 +284,12 @@ struct Runner {
     Raw r;
     r.B = B; r.H = H; r.W = W; r.C = C;
     r.p = (float*)alloc((size_t)B * H * W * C * sizeof(float));
-    if (stats) {
-      r.stats = (double*)salloc((size_t)B * C * 2 * sizeof(double));
-      r.count = (uint32_t*)salloc((size_t)B * ((C + 31) / 32) * sizeof(uint32_t));
-      // one partial row per 32 output pixels is the most any producer writes (StatSink, common.cuh)
-      r.part = (float2*)alloc((size_t)B * (H * W / 32) * C * sizeof(float2));
-    }
+    if (stats) r.stats = (stat_t*)salloc((size_t)B * C * 2 * sizeof(stat_t));
+    return r;
+  }
+  // a reused data buffer with statistics of its own: the accumulators of every layer are zeroed ONCE per forward
+  Raw with_stats(Raw r) {
+    r.stats = (stat_t*)salloc((size_t)r.B * r.C * 2 * sizeof(stat_t));
     return r;
   }
   void tap_act(const char* name, const Act& a, int coff, int C) {
@@ -329,10 +325,8 @@ struct Runner {
     return 2.0 * g.B * g.Hv * g.Wv * (double)g.Cin * g.Cout * g.taps.n;
   }
 
-  // A 3x3 / transposed-conv layer on the tensor-core or the CUDA-core path, by handle precision.  slot_mul / slot_add:
-  // this conv is one of slot_mul convs that together produce the planes of `out` (phases of a transposed conv).
-  int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff, int slot_mul = 1,
-           int slot_add = 0) {
+  // A 3x3 / transposed-conv layer on the tensor-core or the CUDA-core path, by handle precision.
+  int conv(const ConvGeom& g, const Act& in, int in_coff, const LayerW& w, const Raw& out, int out_coff) {
     if (h->prec == AP_PREC_FP32_SIMT) {
       if (ph != PH_EXEC) return AP_OK;
       SimtConvP p{};
@@ -348,7 +342,7 @@ struct Runner {
     if (ph == PH_BUILD) {
       UmmaConv* c = nullptr;
       AP_TRY(umma_conv_create(&c, g, in, in_coff, w.hi, w.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C, out_coff,
-                              out.sink(umma_conv_stat_rows(g) * slot_mul, out_coff), slot_mul, slot_add));
+                              out.stats, out.C, out_coff));
       pl->convs.push_back(c);
       return AP_OK;
     }
@@ -360,7 +354,7 @@ struct Runner {
   int convT(const Act& in, const LayerW& w, const Raw& out, int Hin, int Cin, int Cout) {
     if (h->prec == AP_PREC_FP32_SIMT || !h->convt_packed || w.packT.empty()) {
       for (int ph_ = 0; ph_ < 4; ++ph_)
-        AP_TRY(conv(geom_convT_phase_(pl->B, Hin, Cin, Cout, ph_ >> 1, ph_ & 1), in, 0, w, out, 0, 4, ph_));
+        AP_TRY(conv(geom_convT_phase_(pl->B, Hin, Cin, Cout, ph_ >> 1, ph_ & 1), in, 0, w, out, 0));
       return AP_OK;
     }
     if (ph == PH_SIZE) return AP_OK;
@@ -370,8 +364,8 @@ struct Runner {
       if (ph == PH_BUILD) {
         const ConvGeom g = geom_convT_packed(pl->B, Hin, Cin, pt);
         UmmaConv* c = nullptr;
-        AP_TRY(umma_conv_create(&c, g, in, 0, pt.hi, pt.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C, 0,
-                                out.sink(umma_conv_stat_rows(g) * npack), npack, k, &pt.pk));
+        AP_TRY(umma_conv_create(&c, g, in, 0, pt.hi, pt.lo, h->prec == AP_PREC_FP32X3 ? 3 : 1, out.p, out.C, 0, out.stats,
+                                out.C, 0, &pt.pk));
         pl->convs.push_back(c);
       } else {
         AP_TRY(umma_conv_launch(pl->convs.at(conv_i++), st));
@@ -465,10 +459,7 @@ int Runner::run(const Inputs& in) {
 
   main_st = st;
   ev_i = 0;
-  if (ph == PH_EXEC && pl->sarena_bytes && (prec == AP_PREC_FP32_SIMT || pl->sarena_dirty)) {
-    AP_CUDA(cudaMemsetAsync(pl->sarena, 0, pl->sarena_bytes, st));
-    pl->sarena_dirty = false;
-  }
+  if (ph == PH_EXEC && pl->sarena_bytes) AP_CUDA(cudaMemsetAsync(pl->sarena, 0, pl->sarena_bytes, st));
   cudaStream_t s1 = side(0), s2 = side(1), s3 = side(2);
 
   // trunk buffers: Xb[0] = merge output, Xb[i+1] = output of block i.  The inputs of the three ResnetBlock2 carry
@@ -497,8 +488,8 @@ int Runner::run(const Inputs& in) {
     for (int i = 0; i < nres; ++i) xres[i] = (float*)alloc((size_t)B * 64 * 64 * 256 * sizeof(float));
     for (int i = nres; i < 10; ++i) xres[i] = xres[i & 1];
   }
-  Raw trunk_raw[3];  // conv_block.1, shortcut.0, conv_block.5 of whichever block is running
-  if (!keep) for (int i = 0; i < 3; ++i) trunk_raw[i] = raw(B, 64, 64, 256, true);
+  Raw trunk_raw[3];  // conv_block.1, shortcut.0, conv_block.5 of whichever block is running (data buffers only: the
+  if (!keep) for (int i = 0; i < 3; ++i) trunk_raw[i] = raw(B, 64, 64, 256, false);  // statistics are per layer)
   const size_t encoder_begin = off;
 
   // ---- landmark branch on land1 and land2 as one batch of 2B maps (networks.py:1280-1282, 1331-1332) ----
@@ -597,10 +588,8 @@ int Runner::run(const Inputs& in) {
 
   // ---- merge + 9 residual blocks (networks.py:1251,1330,1333-1337, 2303-2421): stream order; the shortcut conv of a
   // ResnetBlock2 only depends on the block input and runs on a side stream under conv_block.1's apply pass ----
+  // model_tri_merge keeps its bias and has no InstanceNorm (networks.py:1251): no statistics, bias mode
   Raw rM = keep ? raw(B, 64, 64, 256, false) : trunk_raw[0];
-  rM.stats = nullptr;  // model_tri_merge keeps its bias and has no InstanceNorm (networks.py:1251): no statistics, bias mode
-  rM.part = nullptr;
-  rM.count = nullptr;
   AP_TRY(conv(geom_conv(B, 64, 768, 256, 3, 1, 1, 0), MI, 0, W("model_tri_merge"), rM, 0));
   AP_TRY(apply(rM, 0, 256, 0, &Xb[0], 0, 1, h->b_merge, nullptr, nullptr, xres[0], nullptr));
   if (res_from_act) tap_act("merge", Xb[0], 0, 256);
@@ -616,17 +605,17 @@ int Runner::run(const Inputs& in) {
     const Act* dst = &Xb[i + 1];
     const int dst_halo = (i == 8) ? 0 : 1;
     Raw rs;
-    Raw r1 = keep ? raw(B, 64, 64, 256, true) : trunk_raw[0];
+    Raw r1 = keep ? raw(B, 64, 64, 256, true) : with_stats(trunk_raw[0]);
     AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 1), src, 0, W(b + ".conv_block.1"), r1, 0));
     if (b2) {
-      rs = keep ? raw(B, 64, 64, 256, true) : trunk_raw[1];
+      rs = keep ? raw(B, 64, 64, 256, true) : with_stats(trunk_raw[1]);
       AP_TRY(order_after(s1, main_st));
       on(s1);
       AP_TRY(conv(geom_conv(B, 64, cin, 256, 3, 1, 1, 0), src, 0, W(b + ".shortcut.0"), rs, 0));
       on(main_st);
     }
     AP_TRY(apply(r1, 0, 256, 1, &T, 0, 1));
-    Raw r2 = keep ? raw(B, 64, 64, 256, true) : trunk_raw[2];
+    Raw r2 = keep ? raw(B, 64, 64, 256, true) : with_stats(trunk_raw[2]);
     AP_TRY(conv(geom_conv(B, 64, 256, 256, 3, 1, 1, 1), T, 0, W(b + ".conv_block.5"), r2, 0));
     if (b2) AP_TRY(order_after(main_st, s1));
     if (b2) AP_TRY(apply(r2, 0, 256, 0, dst, 0, dst_halo, nullptr, &rs, nullptr, xres[i + 1], nullptr));
@@ -690,9 +679,8 @@ static int get_plan(ap_netg* h, int B, bool shared_photo, Plan** out) {
     delete pl;
     return AP_ERR_CUDA;
   }
-  // halos of zero-padded / never-written regions must read as zero; ticket counters start at zero
-  if (cudaMemset(pl->arena, 0, pl->arena_bytes) != cudaSuccess || cudaMemset(pl->sarena, 0, pl->sarena_bytes) != cudaSuccess ||
-      cudaMemset(pl->d_io, 0, sizeof(IoPtrs)) != cudaSuccess) {
+  // halos of zero-padded / never-written regions must read as zero
+  if (cudaMemset(pl->arena, 0, pl->arena_bytes) != cudaSuccess || cudaMemset(pl->d_io, 0, sizeof(IoPtrs)) != cudaSuccess) {
     delete pl;
     set_error("memset failed");
     return AP_ERR_CUDA;
@@ -963,8 +951,7 @@ static int forward_impl(ap_netg* h, int B, const Inputs& in, cudaStream_t st, co
     h->ev_flops.clear();
     AP_CUDA(cudaEventRecord(h->ev[0], st));
   }
-  const int rc = rx.run(in);
-  if (rc != AP_OK) { pl->sarena_dirty = true; return rc; }
+  AP_TRY(rx.run(in));
   h->last_launches = launches_get() - before;
   h->last_plan = pl;
   return AP_OK;
@@ -1038,6 +1025,25 @@ int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* lan
   AP_TRY(forward_impl(h, B, in, st, pl->ev_in));
   AP_CUDA(cudaMemcpyAsync(out, pl->h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, st));
   AP_CUDA(cudaStreamSynchronize(st));
+  return AP_OK;
+}
+
+int ap_device_enable_peer_access(int device, int peer_device) {
+  int ndev = 0;
+  AP_CUDA(cudaGetDeviceCount(&ndev));
+  AP_REQUIRE(device >= 0 && device < ndev && peer_device >= 0 && peer_device < ndev, AP_ERR_INVALID, "devices %d, %d of %d",
+             device, peer_device, ndev);
+  if (device == peer_device) return AP_OK;
+  int can = 0;
+  AP_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  AP_REQUIRE(can != 0, AP_ERR_UNSUPPORTED, "device %d cannot access the memory of device %d", device, peer_device);
+  int cur = 0;
+  AP_CUDA(cudaGetDevice(&cur));
+  AP_CUDA(cudaSetDevice(device));
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  cudaSetDevice(cur);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return AP_OK; }
+  if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer_device, cudaGetErrorString(e)); return AP_ERR_CUDA; }
   return AP_OK;
 }
 
@@ -1142,8 +1148,6 @@ int ap_conv2d_debug(int impl, int device, int B, int H, int W, int Cin, int Cout
   out.B = B; out.H = Ho; out.W = Ho; out.C = Cout;
   if (rc == AP_OK) rc = dalloc((size_t)B * Ho * Ho * Cout * 4, (void**)&out.p);
   if (rc == AP_OK) rc = dalloc((size_t)B * Cout * 2 * 8, (void**)&out.stats);
-  if (rc == AP_OK && tc) rc = dalloc((size_t)B * (Ho * Ho / 32) * Cout * sizeof(float2), (void**)&out.part);
-  if (rc == AP_OK && tc) rc = dalloc((size_t)B * ((Cout + 31) / 32) * 4, (void**)&out.count);
   std::vector<UmmaConv*> convs;
   if (rc == AP_OK) rc = launch_nchw_to_act(x, in, st);
   if (rc == AP_OK) rc = launch_pack_weights(w, Cout, Cin, ksize, transposed, lw.simt, Cout, 0, lw.hi, lw.lo, st);
@@ -1154,10 +1158,8 @@ int ap_conv2d_debug(int impl, int device, int B, int H, int W, int Cin, int Cout
   if (packed) {
     for (size_t k = 0; k < packT.size() && rc == AP_OK; ++k) {
       UmmaConv* c = nullptr;
-      const ConvGeom gp = geom_convT_packed(B, H, Cin, packT[k]);
-      const int npack = (int)packT.size();
-      rc = umma_conv_create(&c, gp, in, 0, packT[k].hi, packT[k].lo, impl == AP_PREC_FP32X3 ? 3 : 1, out.p, Cout, 0,
-                            out.sink(umma_conv_stat_rows(gp) * npack), npack, (int)k, &packT[k].pk);
+      rc = umma_conv_create(&c, geom_convT_packed(B, H, Cin, packT[k]), in, 0, packT[k].hi, packT[k].lo,
+                            impl == AP_PREC_FP32X3 ? 3 : 1, out.p, Cout, 0, out.stats, Cout, 0, &packT[k].pk);
       if (rc == AP_OK) { convs.push_back(c); rc = umma_conv_launch(c, st); }
     }
   }
@@ -1172,8 +1174,7 @@ int ap_conv2d_debug(int impl, int device, int B, int H, int W, int Cin, int Cout
       rc = launch_conv_simt(p, st);
     } else {
       UmmaConv* c = nullptr;
-      rc = umma_conv_create(&c, g, in, 0, lw.hi, lw.lo, impl == AP_PREC_FP32X3 ? 3 : 1, out.p, Cout, 0,
-                            out.sink(umma_conv_stat_rows(g) * nph), nph, ph);
+      rc = umma_conv_create(&c, g, in, 0, lw.hi, lw.lo, impl == AP_PREC_FP32X3 ? 3 : 1, out.p, Cout, 0, out.stats, Cout, 0);
       if (rc == AP_OK) { convs.push_back(c); rc = umma_conv_launch(c, st); }
     }
   }
@@ -1181,11 +1182,7 @@ int ap_conv2d_debug(int impl, int device, int B, int H, int W, int Cin, int Cout
     ReadP rp{B, Ho, Ho, Cout, FMT_F32, out.p, nullptr, Cout, 0, 0, nullptr, 0, 0, 0, y};
     rc = launch_read(rp, st);
   }
-  if (rc == AP_OK && stats &&
-      cudaMemcpyAsync(stats, out.stats, (size_t)B * Cout * 2 * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-    set_error("stats copy failed");
-    rc = AP_ERR_CUDA;
-  }
+  if (rc == AP_OK && stats) rc = launch_stats_to_double(out.stats, stats, (size_t)B * Cout * 2, st);
   cudaError_t e = cudaStreamSynchronize(st);
   for (UmmaConv* c : convs) umma_conv_destroy(c);
   for (void* p : tmp) cudaFree(p);

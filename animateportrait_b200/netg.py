@@ -220,8 +220,22 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
             self._weights_seen = sig
 
     # ---- the reference interface ----------------------------------------------------------------
-    def forward(self, input, land1, land2, motion, flow, ifmask):
-        """networks.py:1315: returns a new [B, output_nc, 256, 256] fp32 tensor on input's device."""
+    supports_out = True  # forward(..., out=) writes the frames in place (frames.render_frames_sharded uses it)
+
+    def _out_tensor(self, out, B, dev):
+        if out is None:
+            return torch.empty((B, self.output_nc, 256, 256), device=dev, dtype=torch.float32)
+        # `out` may live on ANOTHER GPU of the box (a peer-mapped gather buffer, frames.PeerBuffer): the output kernel
+        # stores through NVLink; the caller has enabled peer access
+        if (tuple(out.shape) != (B, self.output_nc, 256, 256) or out.dtype != torch.float32 or not out.is_cuda
+                or not out.is_contiguous()):
+            raise RuntimeError(f"out: expected a contiguous CUDA fp32 tensor {(B, self.output_nc, 256, 256)}, got "
+                               f"{tuple(out.shape)} {out.dtype} on {out.device}")
+        return out
+
+    def forward(self, input, land1, land2, motion, flow, ifmask, out=None):
+        """networks.py:1315: returns a new [B, output_nc, 256, 256] fp32 tensor on input's device (or fills `out`, an
+        extension the reference does not have)."""
         if not input.is_cuda:
             raise RuntimeError("the B200 generator runs on CUDA tensors only (no CPU fallback); "
                                "use forward_host() for host buffers")
@@ -240,14 +254,14 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
             ts.append(t.detach().to(device=dev, dtype=torch.float32).contiguous())
         with torch.cuda.device(dev):
             self._sync(dev)
-            out = torch.empty((B, self.output_nc, 256, 256), device=dev, dtype=torch.float32)
+            out = self._out_tensor(out, B, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             _capi.check(_capi.lib().ap_netg_forward(self._handle, B, *[C.c_void_p(t.data_ptr()) for t in ts],
                                                     C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "ap_netg_forward")
         return out
 
     @torch.no_grad()
-    def forward_shared_photo(self, input, land1, land2, motion, flow, ifmask):
+    def forward_shared_photo(self, input, land1, land2, motion, flow, ifmask, out=None):
         """Clip form of forward(): `input` is ONE photo [1,3,256,256] and `land1` its landmark map [1,1,256,256], shared
         by the B frames the other four tensors describe (`ap_netg_forward_shared_photo`): the layers that depend on
         them alone run once per call.  Same result as forward(input.expand(B, ...), land1.expand(B, ...), ...)."""
@@ -264,7 +278,7 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
             ts.append(t.detach().to(device=dev, dtype=torch.float32).contiguous())
         with torch.cuda.device(dev):
             self._sync(dev)
-            out = torch.empty((B, self.output_nc, 256, 256), device=dev, dtype=torch.float32)
+            out = self._out_tensor(out, B, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             _capi.check(_capi.lib().ap_netg_forward_shared_photo(self._handle, B, *[C.c_void_p(t.data_ptr()) for t in ts],
                                                                  C.c_void_p(out.data_ptr()), C.c_void_p(stream)),

@@ -105,6 +105,13 @@ int ap_netg_compose(int device, int B, int output_nc, const float* fake_B, const
  *                        that ap_netg_debug_read can return any tap after the forward. */
 int ap_netg_set_option(ap_netg* handle, const char* name, int value);
 
+/* Multi-GPU gather hook: lets kernels running on `device` store into memory of `peer_device` (same
+ * process, or another process's buffer mapped with CUDA IPC).  `out` of ap_netg_forward may then be such memory: the
+ * output kernel of every rank writes its frames straight into ONE buffer on the GPU that owns the clip -- the gather
+ * of the frames costs no copy and no collective.  Replaces nothing in the reference (it is single-GPU,
+ * main_end2end_module2.py:108 passes --gpu_ids 0); idempotent. */
+int ap_device_enable_peer_access(int device, int peer_device);
+
 /* Number of kernels of this library launched (or replayed from the graph) by the most recent forward on this handle. */
 int ap_netg_last_launch_count(ap_netg* handle, int64_t* count);
 
