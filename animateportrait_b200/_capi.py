@@ -30,6 +30,10 @@ SYMBOLS = {
     "ap_netg_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ap_netg_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ap_device_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
+    "ap_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ap_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ap_peer_close": (C.c_int, [C.c_void_p]),
+    "ap_peer_free": (C.c_int, [C.c_void_p]),
     "ap_netg_get_profile": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "ap_netg_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.c_void_p]),

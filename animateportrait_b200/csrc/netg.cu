@@ -1047,6 +1047,60 @@ int ap_device_enable_peer_access(int device, int peer_device) {
   return AP_OK;
 }
 
+// ---- one buffer on the GPU that owns the clip, mapped by every process of the box (CUDA IPC + NVLink peer access) ----
+int ap_peer_alloc(int device, size_t bytes, void** ptr, unsigned char* handle64) {
+  AP_REQUIRE(ptr && handle64 && bytes > 0, AP_ERR_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  int cur = 0;
+  AP_CUDA(cudaGetDevice(&cur));
+  AP_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  cudaIpcMemHandle_t hdl;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hdl, p);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    set_error("peer buffer of %zu bytes on device %d: %s", bytes, device, cudaGetErrorString(e));
+    cudaGetLastError();
+    return AP_ERR_CUDA;
+  }
+  memcpy(handle64, &hdl, 64);
+  *ptr = p;
+  return AP_OK;
+}
+
+int ap_peer_open(int device, const unsigned char* handle64, void** ptr) {
+  AP_REQUIRE(ptr && handle64, AP_ERR_INVALID, "bad argument");
+  cudaIpcMemHandle_t hdl;
+  memcpy(&hdl, handle64, 64);
+  int cur = 0;
+  AP_CUDA(cudaGetDevice(&cur));
+  // opened in the context of the ACCESSING device: the owner's memory is mapped into this device's address space and
+  // peer access to the owner is enabled on the way (what NCCL does for its own NVLink buffers)
+  AP_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) {
+    set_error("cudaIpcOpenMemHandle on device %d: %s", device, cudaGetErrorString(e));
+    cudaGetLastError();
+    return AP_ERR_CUDA;
+  }
+  *ptr = p;
+  return AP_OK;
+}
+
+int ap_peer_close(void* ptr) {
+  if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) { cudaGetLastError(); set_error("cudaIpcCloseMemHandle failed"); return AP_ERR_CUDA; }
+  return AP_OK;
+}
+
+int ap_peer_free(void* ptr) {
+  if (ptr && cudaFree(ptr) != cudaSuccess) { cudaGetLastError(); set_error("cudaFree of a peer buffer failed"); return AP_ERR_CUDA; }
+  return AP_OK;
+}
+
 int ap_netg_last_launch_count(ap_netg* h, int64_t* count) {
   AP_REQUIRE(h && count, AP_ERR_INVALID, "null argument");
   *count = h->last_launches;

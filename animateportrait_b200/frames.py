@@ -119,43 +119,53 @@ def _gather(mine: torch.Tensor, T: int, group, dst: int = 0, out: Optional[torch
 # ----------------------------------------------------------------------------------------------------------
 # one buffer in rank 0's HBM, mapped by every rank of the box (CUDA IPC + NVLink peer access)
 # ----------------------------------------------------------------------------------------------------------
+class _RawCudaArray:
+    """A raw device pointer dressed as a __cuda_array_interface__ object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+_TYPESTR = {torch.float32: "<f4", torch.uint8: "|u1"}
+
+
 class PeerBuffer:
-    """A tensor that lives on rank 0's GPU and is mapped into every rank's address space: kernels of any rank store
-    into it over NVLink.  `tensor` is the mapping of this rank (on rank 0: the buffer itself).  Collective: every
-    rank of `group` constructs it together.  `ok` is False on every rank when any rank could not map it."""
+    """A buffer that lives on rank 0's GPU and is mapped into every rank's address space (CUDA IPC; NVLink peer access
+    enabled by the mapping): kernels of any rank store into it directly.  `tensor` is the mapping of this rank (on rank 0:
+    the buffer itself).  Collective: every rank of `group` constructs it together.  `ok` is False on every rank when any
+    rank could not map it (include/ap_netg.h: ap_peer_alloc / ap_peer_open)."""
 
     def __init__(self, shape, dtype, device: torch.device, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes as C
         from . import _capi
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.tensor: Optional[torch.Tensor] = None
-        self._own = None
+        self._ptr = C.c_void_p()
+        self._owner = self.rank == 0
+        nbytes = int(torch.tensor([], dtype=dtype).element_size())
+        for d in shape:
+            nbytes *= int(d)
         err = ""
         payload = [None]
+        lib = _capi.lib()
         try:
-            if self.rank == 0:
-                self._own = torch.empty(tuple(shape), dtype=dtype, device=device)
-                payload = [reduce_tensor(self._own)]
+            if self._owner:
+                handle = C.create_string_buffer(64)
+                _capi.check(lib.ap_peer_alloc(device.index, max(nbytes, 256), C.byref(self._ptr), handle), "ap_peer_alloc")
+                payload = [handle.raw]
         except Exception as e:  # pragma: no cover - environment dependent
             err = f"export: {e!r}"
         dist.broadcast_object_list(payload, src=_peer(group, 0), group=group)
         try:
-            if self.rank == 0:
-                self.tensor = self._own
-            elif payload[0] is not None:
-                fn, args = payload[0]
-                owner = args[6] if len(args) > 6 else 0  # storage_device of rebuild_cuda_tensor
-                _capi.check(_capi.lib().ap_device_enable_peer_access(device.index, int(owner)), "ap_device_enable_peer_access")
+            if not self._owner:
+                if payload[0] is None:
+                    raise RuntimeError("rank 0 exported nothing")
+                _capi.check(lib.ap_peer_open(device.index, payload[0], C.byref(self._ptr)), "ap_peer_open")
+            if self._ptr.value:
                 with torch.cuda.device(device):
-                    self.tensor = fn(*args)
-                # touch it once from this device: a failure must show up here, not inside a timed step
-                probe = torch.empty(1, dtype=dtype, device=device)
-                probe.copy_(self.tensor.reshape(-1)[:1])
-                torch.cuda.synchronize(device)
-            else:
-                err = err or "rank 0 exported nothing"
+                    self.tensor = torch.as_tensor(_RawCudaArray(self._ptr.value, shape, _TYPESTR[dtype]))
         except Exception as e:  # pragma: no cover - environment dependent
-            err = f"map: {e!r}"
+            err = err or f"map: {e!r}"
             self.tensor = None
         flag = torch.tensor([0 if self.tensor is not None else 1], device=device, dtype=torch.int32)
         dist.all_reduce(flag, group=group)
@@ -164,6 +174,13 @@ class PeerBuffer:
             if err:
                 print(f"[frames] rank {self.rank}: peer buffer unavailable ({err})", file=sys.stderr)
             self.tensor = None
+
+    def close(self) -> None:
+        from . import _capi
+        if self._ptr.value:
+            self.tensor = None
+            (_capi.lib().ap_peer_free if self._owner else _capi.lib().ap_peer_close)(self._ptr)
+            self._ptr.value = None
 
 
 _PEER_CACHE: Dict[tuple, PeerBuffer] = {}

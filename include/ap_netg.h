@@ -112,6 +112,16 @@ int ap_netg_set_option(ap_netg* handle, const char* name, int value);
  * main_end2end_module2.py:108 passes --gpu_ids 0); idempotent. */
 int ap_device_enable_peer_access(int device, int peer_device);
 
+/* The gather buffer itself.  ap_peer_alloc (on the rank that owns the clip): `bytes` of device memory on `device` plus
+ * the 64-byte CUDA IPC handle other processes of the box open it with.  ap_peer_open (every other rank): maps that
+ * memory into the address space of `device`, the GPU whose kernels will store into it, enabling NVLink peer access
+ * to the owner on the way.  ap_peer_close / ap_peer_free undo them.  Plain pointers: the Python side wraps them as
+ * tensors and passes slices of them as `out` of ap_netg_forward. */
+int ap_peer_alloc(int device, size_t bytes, void** ptr, unsigned char* handle64);
+int ap_peer_open(int device, const unsigned char* handle64, void** ptr);
+int ap_peer_close(void* ptr);
+int ap_peer_free(void* ptr);
+
 /* Number of kernels of this library launched (or replayed from the graph) by the most recent forward on this handle. */
 int ap_netg_last_launch_count(ap_netg* handle, int64_t* count);
 
