@@ -228,6 +228,15 @@ void umma_conv_destroy(UmmaConv* c);
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st);
 int umma_init();  // resolves cuTensorMapEncodeTiled, sets the kernel attributes on the current device
 int umma_num_sms();
+// ---- halo-staged trunk conv (conv_halo.cu): 3x3 stride-1 convs on 64x64, N = 256 ----
+struct HaloConv;
+int halo_init_device();
+bool halo_conv_eligible(const ConvGeom& g, const Act& in, int nprod, bool packed);
+int halo_conv_create(HaloConv** out, const ConvGeom& g, const Act& in, int in_coff, const __nv_bfloat16* w_hi,
+                     const __nv_bfloat16* w_lo, int nprod, float* out_raw, int out_C, int out_coff, stat_t* stats,
+                     int stat_C, int stat_coff);
+void halo_conv_destroy(HaloConv* c);
+int halo_conv_launch(const HaloConv* c, cudaStream_t st);
 int stem_umma_init_device();  // per-device kernel attributes of conv_stem.cu / conv_out.cu (called by umma_init)
 int out_umma_init_device();
 int tmap_encode(CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,

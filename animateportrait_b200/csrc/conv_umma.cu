@@ -44,6 +44,7 @@ void launches_add(int n);
 struct alignas(64) UmmaParams {
   CUtensorMap tmA[2];  // hi, lo
   CUtensorMap tmW[2];
+  CUtensorMap tmWs[2];  // the same weights in boxes of 32 rows: N-split items narrower than one 64-row box (small batches)
   CUtensorMap tmO[4];  // fp32 output view(s): one, or one per output phase of a phase-packed transposed conv
   int phase_cols;      // 0, or channels per phase: column block c of the tile goes to tmO[c / phase_cols]
   int ntaps;
@@ -64,6 +65,7 @@ struct alignas(64) UmmaParams {
 struct UmmaConv {
   UmmaParams p;
   int BN, nprod, cg;
+  HaloConv* halo = nullptr;  // the layer runs on the halo-staged kernel instead (conv_halo.cu)
   dim3 grid;
   size_t smem;
 };
@@ -207,7 +209,10 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
         if (item < 0) break;
         const Item w = decode_item1(p, item, BN);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
-        const int nbox = w.bn >> 6;
+        const bool small = w.bn < 64;  // one 32-row box
+        const int nbox = small ? 1 : (w.bn >> 6);
+        const CUtensorMap* mW0 = small ? &p.tmWs[0] : &p.tmW[0];
+        const CUtensorMap* mW1 = small ? &p.tmWs[1] : &p.tmW[1];
         const uint32_t tx_bytes = (NPROD == 3 ? 2u : 1u) * (uint32_t)(A_TILE_BYTES + w.bn * 128);
         for (int it = 0; it < iters; ++it, ++cnt) {
           const uint32_t s = cnt % STAGES;
@@ -222,13 +227,13 @@ __global__ void __launch_bounds__(192, 1) conv_umma1_kernel(const __grid_constan
           if (NPROD == 3) {
             tma_load_4d(sa + A_TILE_BYTES, &p.tmA[1], full, ca, cx, cy, w.img);
             for (int b = 0; b < nbox; ++b) {
-              tma_load_3d(sa + 2 * A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
-              tma_load_3d(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES + b * 8192, &p.tmW[1], full, chunk * 64, w.n0 + 64 * b,
+              tma_load_3d(sa + 2 * A_TILE_BYTES + b * 8192, mW0, full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
+              tma_load_3d(sa + 2 * A_TILE_BYTES + Cfg::W_TILE_BYTES + b * 8192, mW1, full, chunk * 64, w.n0 + 64 * b,
                           p.slab[tap]);
             }
           } else {
             for (int b = 0; b < nbox; ++b)
-              tma_load_3d(sa + A_TILE_BYTES + b * 8192, &p.tmW[0], full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
+              tma_load_3d(sa + A_TILE_BYTES + b * 8192, mW0, full, chunk * 64, w.n0 + 64 * b, p.slab[tap]);
           }
         }
       }
@@ -444,7 +449,9 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
         const Item w = decode_item(p, item, BN, CG, rank);
         const int x0 = w.tx * p.TW * p.stride, y0 = w.ty * p.TH * p.stride;
         const int wrows = w.bn / CG;
-        const int nbox = wrows / Cfg::W_BOX;
+        const bool small = wrows < Cfg::W_BOX;  // one 32-row box per plane
+        const int nbox = small ? 1 : wrows / Cfg::W_BOX;
+        const CUtensorMap* mW = small ? p.tmWs : p.tmW;
         const int wrow0 = w.n0 + rank * wrows;
         const uint32_t tx_bytes = (uint32_t)PLANES * (uint32_t)(A_TILE_BYTES + wrows * 128);
         for (int it = 0; it < iters; ++it, ++cnt) {
@@ -473,8 +480,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
 #pragma unroll
             for (int pl = 0; pl < PLANES; ++pl) {
               const uint32_t dst = sw + pl * Cfg::W_TILE_BYTES + b * (Cfg::W_BOX * 128);
-              if (CG == 2) tma_load_3d_pair(dst, &p.tmW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
-              else tma_load_3d(dst, &p.tmW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
+              if (CG == 2) tma_load_3d_pair(dst, &mW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
+              else tma_load_3d(dst, &mW[pl], full, chunk * 64, wrow0 + Cfg::W_BOX * b, p.slab[tap]);
             }
           }
         }
@@ -706,6 +713,7 @@ int umma_init() {
   g_dev_pairs[dev][2][0] = count_pairs<256, 1>(); g_dev_pairs[dev][2][1] = count_pairs<256, 3>();
   AP_TRY(stem_umma_init_device());
   AP_TRY(out_umma_init_device());
+  AP_TRY(halo_init_device());
   g_dev_ready[dev] = true;
   return AP_OK;
 }
@@ -775,6 +783,13 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   UmmaParams& p = c->p;
   c->BN = g.Cout;
   c->nprod = nprod;
+  if (halo_conv_eligible(g, in, nprod, pk != nullptr)) {
+    const int rc_h = halo_conv_create(&c->halo, g, in, in_coff, w_hi, w_lo, nprod, out_raw, out_C, out_coff,
+                                      (g_dbg & 8) ? nullptr : stats, stat_C, stat_coff);
+    if (rc_h != AP_OK) { delete c; return rc_h; }
+    *out = c;
+    return AP_OK;
+  }
   const int ntiles = (g.Wv / TW) * (g.Hv / TH) * g.B;
   const int pairs = g_pair ? max_pairs(g.Cout, nprod) : 0;
   // measured (profiles/r01_cta_pair.md): pairs win for N = 256 with the 3-product operands (-7..-13%), lose for
@@ -808,6 +823,9 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   const uint32_t wes[3] = {1, 1, 1};
   if (rc == AP_OK) rc = tmap_encode(&p.tmW[0], 0, w_hi, 3, wdims, wstr, wbox, wes);
   if (rc == AP_OK && nprod == 3) rc = tmap_encode(&p.tmW[1], 0, w_lo, 3, wdims, wstr, wbox, wes);
+  const uint32_t wbox_s[3] = {64, 32, 1};
+  if (rc == AP_OK) rc = tmap_encode(&p.tmWs[0], 0, w_hi, 3, wdims, wstr, wbox_s, wes);
+  if (rc == AP_OK && nprod == 3) rc = tmap_encode(&p.tmWs[1], 0, w_lo, 3, wdims, wstr, wbox_s, wes);
   p.phase_cols = pk ? pk->cols : 0;
   if (pk) {
     for (int i = 0; i < pk->nph && rc == AP_OK; ++i)
@@ -839,7 +857,7 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
   const int rem = groups % G;
   int split = 1;
   if (rem > 0) {
-    while (split < 4 && rem * split * 2 <= G && wrows / (split * 2) >= 64) split *= 2;
+    while (split < 4 && rem * split * 2 <= G && wrows / (split * 2) >= 32) split *= 2;  // a part is >= one 32-row box per CTA
   }
   p.split = split;
   p.dbg = g_dbg;
@@ -853,7 +871,10 @@ int umma_conv_create(UmmaConv** out, const ConvGeom& g, const Act& in, int in_co
 
 bool umma_pairs_available() { return umma_init() == AP_OK && g_pair != 0 && max_pairs(256, 3) > 0; }
 
-void umma_conv_destroy(UmmaConv* c) { delete c; }
+void umma_conv_destroy(UmmaConv* c) {
+  if (c && c->halo) halo_conv_destroy(c->halo);
+  delete c;
+}
 
 template <int BN, int NPROD, int CG>
 static int launch_one(const UmmaConv* c, cudaStream_t st) {
@@ -882,6 +903,7 @@ static int launch_one(const UmmaConv* c, cudaStream_t st) {
 }
 
 int umma_conv_launch(const UmmaConv* c, cudaStream_t st) {
+  if (c->halo) return halo_conv_launch(c->halo, st);
 #define AP_UMMA_CASE(BN_, NP_)                                                 \
   if (c->BN == BN_ && c->nprod == NP_)                                         \
     return c->cg == 2 ? launch_one<BN_, NP_, 2>(c, st) : launch_one<BN_, NP_, 1>(c, st);
