@@ -125,6 +125,20 @@ class ClipRenderer:
         return res
 
 
+    @torch.no_grad()
+    def render_to(self, sink, tB_lm_68: torch.Tensor, iw_flow: Optional[torch.Tensor] = None,
+                  if_mask: Optional[torch.Tensor] = None, chunk: Optional[int] = None) -> int:
+        """Render the clip chunk by chunk straight into a `sink.FrameSink` (row f4: the frames reach the encoder's stdin
+        through a pinned ring while the next chunk renders; no PNG files, no frame directory).  Returns the frame count."""
+        T = tB_lm_68.shape[0]
+        step = int(chunk or self.batch)
+        for s in range(0, T, step):
+            e = min(s + step, T)
+            sink.put(self.render(tB_lm_68[s:e], None if iw_flow is None else iw_flow[s:e],
+                                 None if if_mask is None else if_mask[s:e]))
+        return T
+
+
 def render_clip_sharded(renderer: ClipRenderer, tB_lm_68_rank0: Optional[torch.Tensor], T: int, device,
                         iw_flow_rank0: Optional[torch.Tensor] = None, if_mask_rank0: Optional[torch.Tensor] = None,
                         group=None) -> Optional[torch.Tensor]:
