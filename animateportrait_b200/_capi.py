@@ -1,4 +1,4 @@
-"""ctypes binding of libapnetg.so (include/ap_netg.h, include/ap_cond.h). No fallback: a missing or unloadable library raises."""
+"""ctypes binding of libapnetg.so (include/ap_netg.h, include/ap_cond.h, include/ap_flow.h). No fallback: a missing or unloadable library raises."""
 from __future__ import annotations
 
 import ctypes as C
@@ -45,6 +45,13 @@ SYMBOLS = {
     "ap_cond_motion256_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "ap_cond_kp_to_map": (C.c_int, [C.c_int] * 4 + [C.c_float] + [C.c_void_p] * 3),
     "ap_cond_matte_photo": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 5),
+    # include/ap_flow.h
+    "ap_flow_create": (C.c_int, [C.POINTER(C.c_void_p)] + [C.c_int] * 8),
+    "ap_flow_destroy": (C.c_int, [C.c_void_p]),
+    "ap_flow_load_weights": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "ap_flow_forward": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "ap_flow_last_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ap_last_error": (C.c_char_p, []),
     "ap_version": (C.c_char_p, []),
 }

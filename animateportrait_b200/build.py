@@ -16,9 +16,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libapnetg.so")
-SOURCES = ["netg.cu", "conv_umma.cu", "conv_halo.cu", "conv_stem.cu", "conv_out.cu", "landmark.cu", "conv_simt.cu", "elementwise.cu", "compose.cu", "conditioning.cu"]
+SOURCES = ["netg.cu", "conv_umma.cu", "conv_halo.cu", "conv_stem.cu", "conv_out.cu", "landmark.cu", "conv_simt.cu", "elementwise.cu", "compose.cu", "conditioning.cu", "flownet.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"), os.path.join(CSRC, "apply_device.cuh"), os.path.join(os.path.dirname(PKG), "include", "ap_netg.h"),
-           os.path.join(os.path.dirname(PKG), "include", "ap_cond.h")]
+           os.path.join(os.path.dirname(PKG), "include", "ap_cond.h"), os.path.join(os.path.dirname(PKG), "include", "ap_flow.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

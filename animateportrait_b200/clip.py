@@ -16,8 +16,10 @@ Per batch of frames (row f2 + the generator + rows f1/f4), all on the device, on
   * warp_motion = cal_motion256(A_lm_68, tB_lm_68)   (umlvdfw_test_dataset.py:161)
   * fake_B = netG(real_A, A_lm, tB_lm, warp_motion, iw_flow, real_A_if_mask)   (geomcgt_ifw_test_model.py:295)
   * blend with the static drawing + tensor2im -> uint8 HWC frames  (geomcgt_ifw_test_model.py:297-300, util/util.py:9-29)
-iw_flow / real_A_if_mask come from the flow network netF (row f3, not built): they are taken as tensors; when omitted
-the intrinsic-flow branch sees zero flow and a mask of ones (every pixel visible).
+iw_flow / real_A_if_mask come from the flow network netF (row f3): with `netF=` (flownet.FlowUnet) they are computed per
+batch on the device from the same landmarks (flow_network_warp, geomcgt_ifw_test_model.py:62-76; the source key-point
+maps once per photo); they can also be passed as tensors; with neither, the intrinsic-flow branch sees zero flow and a mask
+of ones (every pixel visible).
 """
 from __future__ import annotations
 
@@ -31,10 +33,12 @@ from .frames import _gather, _scatter, shard_range
 
 
 class ClipRenderer:
-    def __init__(self, netG, batch: int = 32, share_photo: bool = True):
+    def __init__(self, netG, batch: int = 32, share_photo: bool = True, netF=None):
         """share_photo: run the photo-only part of the encoder once per batch (`forward_shared_photo`) instead of
-        handing netG B copies of the photo (`forward`, the reference-shaped call); same frames either way."""
+        handing netG B copies of the photo (`forward`, the reference-shaped call); same frames either way.
+        netF: the flow network (flownet.FlowUnet); render() then makes iw_flow / if_mask itself when they are not given."""
         self.netG = netG.module if isinstance(netG, torch.nn.DataParallel) else netG
+        self.netF = netF
         self.batch = int(batch)
         self.share_photo = bool(share_photo)
         self._photo = None
@@ -57,7 +61,10 @@ class ClipRenderer:
         if matte is not None:
             real_A, mask = conditioning.matte_photo(real_A, matte.to(dev))
         land1 = conditioning.draw2(256, 256, lm[None], 3)
-        self._photo = {"real_A": real_A.float().contiguous(), "lm": lm, "land1": land1, "mask": mask,
+        kp1 = None
+        if self.netF is not None:  # source key-point maps of the flow network: frame-invariant
+            kp1 = conditioning.kp_to_map_some((self.netF.size, self.netF.size), lm[None] * 7 / 8)
+        self._photo = {"real_A": real_A.float().contiguous(), "lm": lm, "land1": land1, "mask": mask, "kp1": kp1,
                        "static": None if fakeB_static is None else fakeB_static.to(dev, torch.float32).contiguous(),
                        "expanded": {}}
 
@@ -98,18 +105,22 @@ class ClipRenderer:
             photo, land1, mask, static = self._expanded(B)
             land2 = conditioning.draw2(256, 256, lm[s:e], 3)
             motion = conditioning.cal_motion256(p["lm"], lm[s:e])
-            if iw_flow is None:
-                if zero_flow is None or zero_flow.shape[0] != B:
-                    zero_flow = torch.zeros((B, 2, 256, 256), device=dev)
-                flow = zero_flow
+            if iw_flow is None and if_mask is None and self.netF is not None:
+                kp2 = conditioning.kp_to_map_some((self.netF.size, self.netF.size), lm[s:e] * 7 / 8)
+                flow, ifm = self.netF.warp_tensors(torch.cat([p["kp1"].expand(B, -1, -1, -1), kp2], 1))
             else:
-                flow = iw_flow[s:e]
-            if if_mask is None:
-                if ones_mask is None or ones_mask.shape[0] != B:
-                    ones_mask = torch.ones((B, 1, 256, 256), device=dev)
-                ifm = ones_mask
-            else:
-                ifm = if_mask[s:e]
+                if iw_flow is None:
+                    if zero_flow is None or zero_flow.shape[0] != B:
+                        zero_flow = torch.zeros((B, 2, 256, 256), device=dev)
+                    flow = zero_flow
+                else:
+                    flow = iw_flow[s:e]
+                if if_mask is None:
+                    if ones_mask is None or ones_mask.shape[0] != B:
+                        ones_mask = torch.ones((B, 1, 256, 256), device=dev)
+                    ifm = ones_mask
+                else:
+                    ifm = if_mask[s:e]
             if self.share_photo:
                 fake = self.netG.forward_shared_photo(p["real_A"], p["land1"], land2, motion, flow, ifm)
             else:

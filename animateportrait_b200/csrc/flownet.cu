@@ -1,0 +1,641 @@
+// The intrinsic-flow network netF (`FlowUnet`, Module2/intrinsic_flow_models/networks.py:510-644) and the post-processing of
+// `flow_network_warp` (Module2/models/geomcgt_ifw_test_model.py:62-76) on the GPU: include/ap_flow.h, SURVEY.md §8 row f3.
+//
+// First version on CUDA cores (fp32 FMA): the U-Net's 4x4 stride-2 convolutions live on 112/56/28/14/7-pixel grids that do
+// not tile into the 128-pixel M tiles of the tcgen05 kernels, and the configuration the released checkpoint uses is not known
+// (train_opt.json does not ship), so the network is built from ONE parametric implicit-GEMM kernel:
+//   * `fconv_kernel`: 64 pixels x 64 output channels per CTA, pixels indexed flat over (image, y, x) so that any grid size
+//     works; tap list (7x7, 3x3 s2, 4x4 s2, the four 2x2 phases of ConvTranspose2d(k4,s2,p1) as blockIdx.z); NHWC or NCHW
+//     input.  The normalisation and activation that precede a conv in the reference are applied WHILE ITS OPERAND IS LOADED:
+//     a = act(x * scale[n][c] + shift[n][c]) with act in {LeakyReLU 0.1, LeakyReLU 0.2, ReLU}; zero padding applies to the
+//     activated tensor as in the reference.  Raw conv outputs are what is stored; a skip concatenation is a channel offset.
+//   * BatchNorm (eval): scale/shift come from the checkpoint (gamma / sqrt(var + eps), beta - mean * scale; a conv bias
+//     folds into shift).  InstanceNorm: `fstats_kernel` reduces each raw output plane in a fixed order (deterministic).
+//   * The reference's in-place activations are part of the semantics (networks.py:523,552-568): the skip half of a
+//     concatenation is LeakyReLU_0.2(x), and the parent's in-place ReLU then acts on it -- here simply the activation the
+//     consuming conv applies to those channels.
+//   * `fpost_kernel` / `fresize_kernel`: x2 bilinear up-sampling (align_corners=False), arg-max, mask, rescale and the
+//     align_corners=True resize to 256x256, in PyTorch's op order.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ap_flow.h"
+#include "common.cuh"
+
+namespace ap {
+
+void launches_add(int n);
+int64_t launches_get();
+
+enum { FACT_NONE = 0, FACT_LRELU01 = 1, FACT_LRELU02 = 2, FACT_RELU = 3 };
+
+struct FTap {
+  int8_t dy, dx;
+  uint8_t slab;
+};
+
+struct FConvP {
+  const float* in;     // NHWC [B,Hin,Win,in_C] (channels in_coff .. in_coff+Cin) or NCHW [B,Cin,Hin,Win]
+  int in_nchw, in_C, in_coff;
+  const float* scale;  // [B][in_C] per-image per-channel affine of the operand, or null (identity)
+  const float* shift;
+  int act;
+  const float* w;      // [slab][Cin][CoutP]
+  const float* bias;   // [Cout] or null
+  float* out;          // NHWC [B,Hout,Wout,out_C] at channel out_coff
+  int out_C, out_coff;
+  int B, Hin, Win, Cin, Hv, Wv, stride, Cout, CoutP;
+  int os, Hout, Wout;
+  int nphase, ntaps;   // blockIdx.z = phase: output pixel (y*os + py, x*os + px)
+  int8_t py[4], px[4];
+  FTap taps[4][49];
+};
+
+__device__ __forceinline__ float fact(float v, int act) {
+  if (act == FACT_LRELU01) return v > 0.f ? v : 0.1f * v;
+  if (act == FACT_LRELU02) return v > 0.f ? v : 0.2f * v;
+  if (act == FACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) fconv_kernel(const __grid_constant__ FConvP p) {
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Bs[16][64];
+  const int tid = threadIdx.x;
+  const int HW = p.Hv * p.Wv;
+  const int M = p.B * HW;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64, ph = blockIdx.z;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int Ktot = p.ntaps * p.Cin;
+  const FTap* taps = p.taps[ph];
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // operand loader: thread -> (pixel lm, k offsets kk0, kk0 + 4, ...)
+  const int lm = tid & 63;
+  const int m = m0 + lm;
+  const bool m_ok = m < M;
+  const int img = m_ok ? m / HW : 0;
+  const int pix = m_ok ? m - img * HW : 0;
+  const int vy = pix / p.Wv, vx = pix - vy * p.Wv;
+
+  for (int k0 = 0; k0 < Ktot; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = (tid >> 6) + 4 * i;
+      const int k = k0 + kk;
+      float v = 0.f;
+      if (m_ok && k < Ktot) {
+        const int t = k / p.Cin;
+        const int c = k - t * p.Cin;
+        const int iy = vy * p.stride + taps[t].dy, ix = vx * p.stride + taps[t].dx;
+        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
+          if (p.in_nchw) v = p.in[((size_t)(img * p.Cin + c) * p.Hin + iy) * p.Win + ix];
+          else v = p.in[((size_t)(img * p.Hin + iy) * p.Win + ix) * p.in_C + p.in_coff + c];
+          if (p.scale) v = fmaf(v, p.scale[(size_t)img * p.in_C + p.in_coff + c], p.shift[(size_t)img * p.in_C + p.in_coff + c]);
+          v = fact(v, p.act);
+        }
+      }
+      As[kk][lm] = v;
+    }
+    {
+      const int kk = tid >> 4;
+      const int k = k0 + kk;
+      const int col = (tid & 15) * 4;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < Ktot && n0 + col < p.CoutP) {
+        const int t = k / p.Cin;
+        const int c = k - t * p.Cin;
+        w = *reinterpret_cast<const float4*>(p.w + ((size_t)taps[t].slab * p.Cin + c) * p.CoutP + n0 + col);
+      }
+      *reinterpret_cast<float4*>(&Bs[kk][col]) = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+    const int im = mm / HW, pm = mm - im * HW;
+    const int y = pm / p.Wv, x = pm - y * p.Wv;
+    const int oy = y * p.os + p.py[ph], ox = x * p.os + p.px[ph];
+    float* dst = p.out + ((size_t)(im * p.Hout + oy) * p.Wout + ox) * p.out_C + p.out_coff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.Cout) dst[n] = acc[i][j] + (p.bias ? p.bias[n] : 0.f);
+    }
+  }
+}
+
+// InstanceNorm2d(affine=False) of a raw NHWC plane as an operand transform: scale = rstd, shift = -mean * rstd.
+// One CTA per (image, 32-channel group): 8 pixel lanes x 32 channels, then the 8 partial sums in a fixed order.
+__global__ void __launch_bounds__(256) fstats_kernel(const float* __restrict__ x, int HW, int C, int coff, int nC, float* scale,
+                                                     float* shift) {
+  __shared__ double ssum[8][32], ssq[8][32];
+  const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+  double s = 0.0, q = 0.0;
+  if (c < nC) {
+    const float* src = x + (size_t)n * HW * C + coff + c;
+    for (int p = r; p < HW; p += 8) {
+      const double v = (double)src[(size_t)p * C];
+      s += v;
+      q += v * v;
+    }
+  }
+  ssum[r][threadIdx.x & 31] = s;
+  ssq[r][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (r == 0 && c < nC) {
+    for (int k = 1; k < 8; ++k) { s += ssum[k][threadIdx.x]; q += ssq[k][threadIdx.x]; }
+    const double mean = s / HW;
+    double var = q / HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = 1.0f / sqrtf((float)var + 1e-5f);
+    scale[(size_t)n * C + coff + c] = rstd;
+    shift[(size_t)n * C + coff + c] = -(float)mean * rstd;
+  }
+}
+
+__global__ void fbroadcast_kernel(const float* __restrict__ sc, const float* __restrict__ sh, int C, int coff, int nC, int B,
+                                  float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * nC) return;
+  const int n = i / nC, c = i - n * nC;
+  scale[(size_t)n * C + coff + c] = sc[c];
+  shift[(size_t)n * C + coff + c] = sh[c];
+}
+
+// upsample_bilinear2d(align_corners=False), scale factor 2: src = 0.5 * (dst + 0.5) - 0.5, clamped at 0
+struct FLerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ FLerp flerp_half(int dst, int in_size) {
+  float real = __fsub_rn(__fmul_rn(0.5f, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  if (real < 0.f) real = 0.f;
+  FLerp r;
+  r.i0 = (int)real;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = __fsub_rn(real, (float)r.i0);
+  r.l0 = __fsub_rn(1.f, r.l1);
+  return r;
+}
+__device__ __forceinline__ FLerp flerp_ac(int dst, float scale, int in_size) {  // align_corners=True: src = scale * dst
+  const float real = __fmul_rn(scale, (float)dst);
+  FLerp r;
+  r.i0 = (int)real;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = fminf(fmaxf(__fsub_rn(real, (float)r.i0), 0.f), 1.f);
+  r.l0 = __fsub_rn(1.f, r.l1);
+  return r;
+}
+__device__ __forceinline__ float fbilerp(float v00, float v01, float v10, float v11, const FLerp& ly, const FLerp& lx) {
+  const float top = __fadd_rn(__fmul_rn(lx.l0, v00), __fmul_rn(lx.l1, v01));
+  const float bot = __fadd_rn(__fmul_rn(lx.l0, v10), __fmul_rn(lx.l1, v11));
+  return __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+}
+
+// heads [B,s,s,8] (channels 0,1 = flow, 2..4 = visibility) -> flow_out [B,2,R,R], vis_out [B,3,R,R] (optional) and the
+// masked, rescaled flow fm [B,2,R,R] / mask mk [B,1,R,R] of flow_network_warp (geomcgt_ifw_test_model.py:69-73), R = 2s
+__global__ void fpost_kernel(const float* __restrict__ heads, int B, int s, float* flow_out, float* vis_out, float* fm, float* mk) {
+  const int R = 2 * s;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * R * R) return;
+  const int x = i % R, y = (i / R) % R, n = i / (R * R);
+  const FLerp ly = flerp_half(y, s), lx = flerp_half(x, s);
+  const float* h = heads + (size_t)n * s * s * 8;
+  float v[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c)
+    v[c] = fbilerp(h[((size_t)ly.i0 * s + lx.i0) * 8 + c], h[((size_t)ly.i0 * s + lx.i1) * 8 + c],
+                   h[((size_t)ly.i1 * s + lx.i0) * 8 + c], h[((size_t)ly.i1 * s + lx.i1) * 8 + c], ly, lx);
+  const size_t plane = (size_t)R * R, o = (size_t)y * R + x;
+  if (flow_out) { flow_out[((size_t)n * 2 + 0) * plane + o] = v[0]; flow_out[((size_t)n * 2 + 1) * plane + o] = v[1]; }
+  if (vis_out) {
+    vis_out[((size_t)n * 3 + 0) * plane + o] = v[2];
+    vis_out[((size_t)n * 3 + 1) * plane + o] = v[3];
+    vis_out[((size_t)n * 3 + 2) * plane + o] = v[4];
+  }
+  // argmax over the three visibility classes (first maximum wins, like torch.argmax); mask = class < 2
+  int am = 0;
+  float best = v[2];
+  if (v[3] > best) { best = v[3]; am = 1; }
+  if (v[4] > best) { am = 2; }
+  const float mask = am < 2 ? 1.f : 0.f;
+  if (fm) {
+    // flow_out * 20. * mask, then / 7 * 8
+    fm[((size_t)n * 2 + 0) * plane + o] = __fmul_rn(__fdiv_rn(__fmul_rn(__fmul_rn(v[0], 20.f), mask), 7.f), 8.f);
+    fm[((size_t)n * 2 + 1) * plane + o] = __fmul_rn(__fdiv_rn(__fmul_rn(__fmul_rn(v[1], 20.f), mask), 7.f), 8.f);
+    mk[(size_t)n * plane + o] = mask;
+  }
+}
+
+// F.interpolate(x, size=(256,256), mode='bilinear', align_corners=True) of NCHW planes
+__global__ void fresize_kernel(const float* __restrict__ src, int planes, int R, float* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes * 65536) return;
+  const int x = i & 255, y = (i >> 8) & 255, pl = i >> 16;
+  const float scale = (float)(R - 1) / 255.f;
+  const FLerp ly = flerp_ac(y, scale, R), lx = flerp_ac(x, scale, R);
+  const float* s = src + (size_t)pl * R * R;
+  dst[i] = fbilerp(s[(size_t)ly.i0 * R + lx.i0], s[(size_t)ly.i0 * R + lx.i1], s[(size_t)ly.i1 * R + lx.i0],
+                   s[(size_t)ly.i1 * R + lx.i1], ly, lx);
+}
+
+}  // namespace ap
+
+using namespace ap;
+
+// =================================================================================================
+// host side
+// =================================================================================================
+namespace {
+
+struct FLayerW {
+  float* w = nullptr;     // [slab][Cin][CoutP]
+  float* bias = nullptr;  // [Cout] applied in the conv epilogue, or null
+  float* nsc = nullptr;   // BatchNorm: per-channel scale / shift of the OUTPUT of this conv (bias folded in)
+  float* nsh = nullptr;
+  int cout = 0, cin = 0, k = 0, coutp = 0;
+  bool transposed = false;
+};
+
+struct FBuf {
+  float* p = nullptr;
+  float* scale = nullptr;  // [B][C]
+  float* shift = nullptr;
+  int H = 0, C = 0;
+};
+
+}  // namespace
+
+struct ap_flow {
+  int input_nc = 136, nf = 16, start_scale = 2, num_scale = 4, norm = 0, max_nf = 512, size = 224, device = 0;
+  int ndown = 0;                      // stride-2 convs of conv_downsample
+  std::vector<int> outer, inner, sz;  // per level: channels, input size of the level
+  std::map<std::string, FLayerW> w;
+  std::vector<void*> owned;
+  bool loaded = false;
+  // workspace of the current batch size
+  int planB = 0;
+  std::vector<void*> ws;
+  std::vector<FBuf> cds;   // conv_downsample outputs
+  std::vector<FBuf> cat;   // cat[l] (l >= 1): [d_{l-1} | u_l]; cat[0] = u_0
+  FBuf dinner, heads;
+  float *fm = nullptr, *mk = nullptr;
+  int64_t last_launches = 0;
+};
+
+static std::string level_prefix(int l) {
+  std::string s = "unet_block.";
+  for (int i = 0; i < l; ++i) s += "submodule.";
+  return s;
+}
+
+static void flow_free_ws(ap_flow* h) {
+  for (void* p : h->ws) cudaFree(p);
+  h->ws.clear();
+  h->cds.clear();
+  h->cat.clear();
+  h->planB = 0;
+}
+
+static int flow_alloc(ap_flow* h, size_t bytes, void** p) {
+  AP_CUDA(cudaMalloc(p, bytes));
+  h->ws.push_back(*p);
+  return AP_OK;
+}
+
+static int flow_buf(ap_flow* h, int B, int H, int C, FBuf* b) {
+  b->H = H; b->C = C;
+  AP_TRY(flow_alloc(h, (size_t)B * H * H * C * 4, (void**)&b->p));
+  AP_TRY(flow_alloc(h, (size_t)B * C * 4, (void**)&b->scale));
+  AP_TRY(flow_alloc(h, (size_t)B * C * 4, (void**)&b->shift));
+  return AP_OK;
+}
+
+static int flow_plan(ap_flow* h, int B) {
+  if (h->planB == B) return AP_OK;
+  AP_CUDA(cudaDeviceSynchronize());
+  flow_free_ws(h);
+  const int L = h->num_scale;
+  int s = h->size, c = h->nf;
+  h->cds.resize(h->ndown + 1);
+  AP_TRY(flow_buf(h, B, s, c, &h->cds[0]));
+  for (int i = 0; i < h->ndown; ++i) {
+    s /= 2; c *= 2;
+    AP_TRY(flow_buf(h, B, s, c, &h->cds[i + 1]));
+  }
+  h->cat.resize(L);
+  for (int l = 0; l < L; ++l) AP_TRY(flow_buf(h, B, h->sz[l], l == 0 ? h->outer[0] : 2 * h->outer[l], &h->cat[l]));
+  AP_TRY(flow_buf(h, B, h->sz[L - 1] / 2, h->inner[L - 1], &h->dinner));
+  AP_TRY(flow_buf(h, B, h->sz[0], 8, &h->heads));
+  const int R = 2 * h->sz[0];
+  AP_TRY(flow_alloc(h, (size_t)B * 2 * R * R * 4, (void**)&h->fm));
+  AP_TRY(flow_alloc(h, (size_t)B * R * R * 4, (void**)&h->mk));
+  h->planB = B;
+  return AP_OK;
+}
+
+// taps of a k x k conv with padding `pad`
+static void taps_conv(FConvP* p, int k, int pad) {
+  p->nphase = 1; p->ntaps = k * k; p->os = 1; p->py[0] = p->px[0] = 0;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) p->taps[0][ky * k + kx] = FTap{(int8_t)(ky - pad), (int8_t)(kx - pad), (uint8_t)(ky * k + kx)};
+}
+// ConvTranspose2d(k4, s2, p1): output (2y + py, 2x + px) = sum over input rows y + dy with kernel row ky:
+//   py = 0: (ky 1, dy 0), (ky 3, dy -1);   py = 1: (ky 2, dy 0), (ky 0, dy +1); same along x
+static void taps_convT4(FConvP* p) {
+  static const int KY[2][2] = {{1, 3}, {2, 0}}, DY[2][2] = {{0, -1}, {0, 1}};
+  p->nphase = 4; p->ntaps = 4; p->os = 2;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    p->py[ph] = (int8_t)py; p->px[ph] = (int8_t)px;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        p->taps[ph][a * 2 + b] = FTap{(int8_t)DY[py][a], (int8_t)DY[px][b], (uint8_t)(KY[py][a] * 4 + KY[px][b])};
+  }
+}
+
+static int flow_conv(ap_flow* h, int B, const float* in, int in_nchw, int in_C, int in_coff, const float* scale,
+                     const float* shift, int act, int Hin, const FLayerW& w, int stride, int transposed4, int pad, float* out,
+                     int out_C, int out_coff, int Hout, cudaStream_t st) {
+  FConvP p;
+  memset(&p, 0, sizeof(p));
+  p.in = in; p.in_nchw = in_nchw; p.in_C = in_C; p.in_coff = in_coff; p.scale = scale; p.shift = shift; p.act = act;
+  p.w = w.w; p.bias = w.bias; p.out = out; p.out_C = out_C; p.out_coff = out_coff;
+  p.B = B; p.Hin = Hin; p.Win = Hin; p.Cin = w.cin; p.Cout = w.cout; p.CoutP = w.coutp;
+  p.Hout = Hout; p.Wout = Hout;
+  if (transposed4) {
+    taps_convT4(&p);
+    p.Hv = Hin; p.Wv = Hin; p.stride = 1;
+  } else {
+    taps_conv(&p, w.k, pad);
+    p.Hv = Hout; p.Wv = Hout; p.stride = stride;
+  }
+  const int M = B * p.Hv * p.Wv;
+  dim3 grid((M + 63) / 64, (w.cout + 63) / 64, p.nphase);
+  fconv_kernel<<<grid, 256, 0, st>>>(p);
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  return AP_OK;
+}
+
+// operand transform of buffer channels [coff, coff + nC): the producing conv's normalisation
+static int flow_norm(ap_flow* h, int B, const FBuf& b, int coff, int nC, const FLayerW& w, cudaStream_t st) {
+  if (h->norm == 0) {
+    fbroadcast_kernel<<<(B * nC + 255) / 256, 256, 0, st>>>(w.nsc, w.nsh, b.C, coff, nC, B, b.scale, b.shift);
+  } else {
+    fstats_kernel<<<dim3((nC + 31) / 32, B), 256, 0, st>>>(b.p, b.H * b.H, b.C, coff, nC, b.scale, b.shift);
+  }
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  return AP_OK;
+}
+
+extern "C" {
+
+int ap_flow_create(ap_flow** handle, int input_nc, int nf, int start_scale, int num_scale, int norm, int max_nf, int size,
+                   int device) {
+  AP_REQUIRE(handle != nullptr, AP_ERR_INVALID, "null handle pointer");
+  AP_REQUIRE(input_nc >= 1 && nf >= 4 && nf % 4 == 0 && num_scale >= 1 && num_scale <= 8 && (norm == 0 || norm == 1) &&
+                 max_nf >= nf && size >= 8,
+             AP_ERR_INVALID, "FlowUnet(input_nc=%d, nf=%d, num_scale=%d, norm=%d, max_nf=%d, size=%d)", input_nc, nf, num_scale,
+             norm, max_nf, size);
+  AP_REQUIRE(start_scale == 1 || start_scale == 2 || start_scale == 4 || start_scale == 8, AP_ERR_INVALID, "start_scale=%d",
+             start_scale);
+  int ndev = 0;
+  AP_CUDA(cudaGetDeviceCount(&ndev));
+  AP_REQUIRE(device >= 0 && device < ndev, AP_ERR_INVALID, "device %d of %d", device, ndev);
+  ap_flow* h = new ap_flow();
+  h->input_nc = input_nc; h->nf = nf; h->start_scale = start_scale; h->num_scale = num_scale; h->norm = norm;
+  h->max_nf = max_nf; h->size = size; h->device = device;
+  int s = size, nc = nf;
+  for (int sc = start_scale; sc > 1; sc /= 2) {
+    s = (s + 2 - 3) / 2 + 1;
+    nc *= 2;
+    ++h->ndown;
+  }
+  for (int l = 0; l < num_scale; ++l) {
+    if (s % 2 != 0 || s < 2) {
+      delete h;
+      set_error("FlowUnet: level %d works on %dx%d, which a 4x4 stride-2 conv and its transpose do not round-trip (the reference "
+                "fails in torch.cat for this configuration)", l, s, s);
+      return AP_ERR_UNSUPPORTED;
+    }
+    long long o = (long long)nc << l, i = (long long)nc << (l + 1);
+    h->outer.push_back((int)(o < max_nf ? o : max_nf));
+    h->inner.push_back((int)(i < max_nf ? i : max_nf));
+    h->sz.push_back(s);
+    s /= 2;
+  }
+  *handle = h;
+  return AP_OK;
+}
+
+int ap_flow_destroy(ap_flow* h) {
+  if (!h) return AP_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  flow_free_ws(h);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return AP_OK;
+}
+
+int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const float* const* ptrs, const int64_t* shapes,
+                         int on_device, void* cuda_stream) {
+  AP_REQUIRE(h && names && ptrs && shapes, AP_ERR_INVALID, "null argument");
+  AP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  std::map<std::string, int> idx;
+  for (int i = 0; i < n; ++i) idx[names[i]] = i;
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  h->w.clear();
+  h->loaded = false;
+  const bool inorm = h->norm == 1;
+  std::vector<void*> staging;
+  auto host_copy = [&](const std::string& key, size_t elems, std::vector<float>* out) -> int {
+    auto it = idx.find(key);
+    AP_REQUIRE(it != idx.end(), AP_ERR_INVALID, "missing key %s", key.c_str());
+    const int64_t* sh = shapes + 4 * it->second;
+    AP_REQUIRE((size_t)(sh[0] * sh[1] * sh[2] * sh[3]) == elems, AP_ERR_INVALID, "size mismatch for %s", key.c_str());
+    out->resize(elems);
+    if (on_device) AP_CUDA(cudaMemcpy(out->data(), ptrs[it->second], elems * 4, cudaMemcpyDeviceToHost));
+    else memcpy(out->data(), ptrs[it->second], elems * 4);
+    return AP_OK;
+  };
+  auto upload = [&](const std::vector<float>& v, float** dst) -> int {
+    AP_CUDA(cudaMalloc((void**)dst, v.size() * 4));
+    h->owned.push_back(*dst);
+    AP_CUDA(cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    return AP_OK;
+  };
+  // conv `key` (Cout x Cin x k x k, or transposed Cin x Cout x k x k); `normkey` = its BatchNorm ("" = no norm after it);
+  // bias_mode: 0 none, 1 epilogue bias (no norm follows), 2 bias in the checkpoint folds into the norm (or cancels)
+  auto add = [&](const std::string& name, const std::string& key, int cout, int cin, int k, bool transposed,
+                 const std::string& normkey, bool has_bias) -> int {
+    FLayerW lw;
+    lw.cout = cout; lw.cin = cin; lw.k = k; lw.transposed = transposed; lw.coutp = (cout + 3) / 4 * 4;
+    std::vector<float> wt, packed((size_t)k * k * cin * lw.coutp, 0.f), bias;
+    AP_TRY(host_copy(key + ".weight", (size_t)cout * cin * k * k, &wt));
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int sl = 0; sl < k * k; ++sl) {
+          const size_t s_ = transposed ? (((size_t)ci * cout + co) * k * k + sl) : (((size_t)co * cin + ci) * k * k + sl);
+          packed[((size_t)sl * cin + ci) * lw.coutp + co] = wt[s_];
+        }
+    AP_TRY(upload(packed, &lw.w));
+    if (has_bias) AP_TRY(host_copy(key + ".bias", cout, &bias));
+    if (normkey.empty()) {
+      if (has_bias) AP_TRY(upload(bias, &lw.bias));
+    } else if (!inorm) {
+      // BatchNorm2d in eval mode: y = x * (gamma * invstd) + (beta - mean * gamma * invstd); a conv bias folds into the shift
+      std::vector<float> g, b, mu, var, sc(cout), sh(cout);
+      AP_TRY(host_copy(normkey + ".weight", cout, &g));
+      AP_TRY(host_copy(normkey + ".bias", cout, &b));
+      AP_TRY(host_copy(normkey + ".running_mean", cout, &mu));
+      AP_TRY(host_copy(normkey + ".running_var", cout, &var));
+      for (int c = 0; c < cout; ++c) {
+        const float invstd = 1.0f / sqrtf(var[c] + 1e-5f);
+        sc[c] = g[c] * invstd;
+        sh[c] = b[c] - mu[c] * sc[c] + (has_bias ? bias[c] * sc[c] : 0.f);
+      }
+      AP_TRY(upload(sc, &lw.nsc));
+      AP_TRY(upload(sh, &lw.nsh));
+    }  // InstanceNorm: the bias cancels, the statistics come from the data
+    h->w[name] = lw;
+    return AP_OK;
+  };
+  int nc = h->nf;
+  AP_TRY(add("cds0", "conv_downsample.0", h->nf, h->input_nc, 7, false, "conv_downsample.1", inorm));
+  for (int i = 0; i < h->ndown; ++i) {
+    AP_TRY(add("cds" + std::to_string(i + 1), "conv_downsample." + std::to_string(3 * (i + 1)), 2 * nc, nc, 3, false,
+               "conv_downsample." + std::to_string(3 * (i + 1) + 1), inorm));
+    nc *= 2;
+  }
+  const int L = h->num_scale;
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = level_prefix(l);
+    const bool outermost = l == 0, innermost = l == L - 1;
+    const std::string dk = pre + "down." + std::to_string(outermost ? 0 : 1);
+    AP_TRY(add("down" + std::to_string(l), dk, h->inner[l], h->outer[l], 4, false,
+               innermost ? "" : pre + "down." + std::to_string(outermost ? 1 : 2), inorm));
+    AP_TRY(add("up" + std::to_string(l), pre + "up.1", h->outer[l], innermost ? h->inner[l] : 2 * h->inner[l], 4, true,
+               pre + "up.2", outermost ? true : inorm));
+  }
+  // the two heads the caller uses (flow at the outermost level, visibility) as ONE conv with 5 output channels
+  {
+    std::vector<float> wf, wv, bf, bv;
+    const int cin = h->outer[0];
+    AP_TRY(host_copy("unet_block.predict_flow.1.weight", (size_t)2 * cin * 9, &wf));
+    AP_TRY(host_copy("unet_block.predict_flow.1.bias", 2, &bf));
+    AP_TRY(host_copy("predict_vis.1.weight", (size_t)3 * cin * 9, &wv));
+    AP_TRY(host_copy("predict_vis.1.bias", 3, &bv));
+    FLayerW lw;
+    lw.cout = 5; lw.cin = cin; lw.k = 3; lw.coutp = 8;
+    std::vector<float> packed((size_t)9 * cin * 8, 0.f), bias(5);
+    for (int co = 0; co < 5; ++co) {
+      const std::vector<float>& src = co < 2 ? wf : wv;
+      const int c_ = co < 2 ? co : co - 2;
+      for (int ci = 0; ci < cin; ++ci)
+        for (int sl = 0; sl < 9; ++sl) packed[((size_t)sl * cin + ci) * 8 + co] = src[((size_t)c_ * cin + ci) * 9 + sl];
+      bias[co] = co < 2 ? bf[co] : bv[co - 2];
+    }
+    AP_TRY(upload(packed, &lw.w));
+    AP_TRY(upload(bias, &lw.bias));
+    h->w["heads"] = lw;
+  }
+  (void)st;
+  flow_free_ws(h);
+  h->loaded = true;
+  return AP_OK;
+}
+
+int ap_flow_forward(ap_flow* h, int B, const float* kp_maps, float* flow_out, float* vis_out, float* iw_flow, float* if_mask,
+                    void* cuda_stream) {
+  AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1 && kp_maps, AP_ERR_INVALID, "bad argument");
+  AP_REQUIRE((iw_flow == nullptr) == (if_mask == nullptr), AP_ERR_INVALID, "iw_flow and if_mask come together");
+  AP_CUDA(cudaSetDevice(h->device));
+  AP_TRY(flow_plan(h, B));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t before = launches_get();
+  const int L = h->num_scale;
+  // conv_downsample: conv7x7 + norm + LeakyReLU(0.1), then 3x3 stride-2 convs (networks.py:601-612)
+  AP_TRY(flow_conv(h, B, kp_maps, 1, h->input_nc, 0, nullptr, nullptr, FACT_NONE, h->size, h->w.at("cds0"), 1, 0, 3,
+                   h->cds[0].p, h->cds[0].C, 0, h->size, st));
+  AP_TRY(flow_norm(h, B, h->cds[0], 0, h->cds[0].C, h->w.at("cds0"), st));
+  for (int i = 0; i < h->ndown; ++i) {
+    const FBuf& src = h->cds[i];
+    const FBuf& dst = h->cds[i + 1];
+    const FLayerW& w = h->w.at("cds" + std::to_string(i + 1));
+    AP_TRY(flow_conv(h, B, src.p, 0, src.C, 0, src.scale, src.shift, FACT_LRELU01, src.H, w, 2, 0, 1, dst.p, dst.C, 0, dst.H, st));
+    AP_TRY(flow_norm(h, B, dst, 0, dst.C, w, st));
+  }
+  // encoder: level l reads x_l (x_0 = LeakyReLU_0.1(norm(.)); x_l = LeakyReLU_0.2(norm(d_{l-1})) -- the in-place activation
+  // at the head of `down`, networks.py:523) and writes d_l into the first half of the next level's concatenation buffer
+  for (int l = 0; l < L; ++l) {
+    const FBuf& src = l == 0 ? h->cds[h->ndown] : h->cat[l];
+    const FLayerW& w = h->w.at("down" + std::to_string(l));
+    const bool innermost = l == L - 1;
+    const FBuf& dst = innermost ? h->dinner : h->cat[l + 1];
+    AP_TRY(flow_conv(h, B, src.p, 0, src.C, 0, src.scale, src.shift, l == 0 ? FACT_LRELU01 : FACT_LRELU02, src.H, w, 2, 0, 1,
+                     dst.p, dst.C, 0, dst.H, st));
+    if (!innermost) AP_TRY(flow_norm(h, B, dst, 0, w.cout, w, st));
+  }
+  // decoder: u_l = norm(ConvT(ReLU(.))) of the whole concatenation of the level below (or of the innermost d)
+  for (int l = L - 1; l >= 0; --l) {
+    const bool innermost = l == L - 1;
+    const FBuf& src = innermost ? h->dinner : h->cat[l + 1];
+    const FLayerW& w = h->w.at("up" + std::to_string(l));
+    const FBuf& dst = h->cat[l];
+    const int coff = l == 0 ? 0 : h->outer[l];
+    AP_TRY(flow_conv(h, B, src.p, 0, src.C, 0, innermost ? nullptr : src.scale, innermost ? nullptr : src.shift, FACT_RELU,
+                     src.H, w, 1, 1, 0, dst.p, dst.C, coff, dst.H, st));
+    AP_TRY(flow_norm(h, B, dst, coff, w.cout, w, st));
+  }
+  // heads on LeakyReLU_0.1(u_0): predict_flow of the outermost block + predict_vis (networks.py:571-573, 622-625)
+  AP_TRY(flow_conv(h, B, h->cat[0].p, 0, h->cat[0].C, 0, h->cat[0].scale, h->cat[0].shift, FACT_LRELU01, h->cat[0].H,
+                   h->w.at("heads"), 1, 0, 1, h->heads.p, 8, 0, h->heads.H, st));
+  const int s = h->sz[0], R = 2 * s;
+  fpost_kernel<<<(B * R * R + 255) / 256, 256, 0, st>>>(h->heads.p, B, s, flow_out, vis_out, iw_flow ? h->fm : nullptr, h->mk);
+  AP_CUDA(cudaGetLastError());
+  launches_add(1);
+  if (iw_flow) {
+    fresize_kernel<<<(B * 2 * 65536 + 255) / 256, 256, 0, st>>>(h->fm, B * 2, R, iw_flow);
+    fresize_kernel<<<(B * 65536 + 255) / 256, 256, 0, st>>>(h->mk, B, R, if_mask);
+    AP_CUDA(cudaGetLastError());
+    launches_add(2);
+  }
+  h->last_launches = launches_get() - before;
+  return AP_OK;
+}
+
+int ap_flow_last_launch_count(ap_flow* h, int64_t* count) {
+  AP_REQUIRE(h && count, AP_ERR_INVALID, "null argument");
+  *count = h->last_launches;
+  return AP_OK;
+}
+
+}  // extern "C"

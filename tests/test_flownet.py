@@ -1,0 +1,140 @@
+"""netF, the intrinsic-flow network (include/ap_flow.h, animateportrait_b200/flownet.py).
+
+CPU: the oracle restatement against the golden vectors generated from the reference class itself
+(tests/golden/make_flow_golden.py), the checkpoint layout of the host module against the oracle's spec (which that script
+checked against the real module's state_dict), configuration errors.
+GPU (-m gpu): the CUDA path through the C ABI against the oracle for every golden configuration: flow / visibility within
+1e-3 max-abs (the fp32 gate of the path), the 256x256 tensors the generator consumes, `flow_network_warp` from landmarks."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from animateportrait_b200.flownet import FlowUnet, flow_network_warp
+from oracle import cond_oracle as OC
+from oracle import flow_oracle as FO
+from tests.golden.make_flow_golden import CASES, kp_maps
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _seed(name):
+    return sum(map(ord, name)) % 1000
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_the_reference_vectors(name):
+    nf, ss, ns, norm, B = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sd = FO.make_state_dict(136, nf, ss, ns, norm, seed=int(g["seed"]))
+    flow, vis, _, _ = FO.flow_unet_forward(sd, kp_maps(B, seed=7 + B), nf, ss, ns, norm)
+    iw, ifm = FO.warp_outputs(flow, vis)
+    assert np.array_equal(flow[:, :, ::4, ::4].numpy(), g["flow"]) and np.array_equal(vis[:, :, ::4, ::4].numpy(), g["vis"])
+    assert np.array_equal(iw[:, :, ::4, ::4].numpy(), g["iw_flow"]) and np.array_equal(ifm[:, :, ::4, ::4].numpy(), g["if_mask"])
+    assert abs(float(flow.double().abs().sum()) - float(g["flow_abs_sum"])) <= 1e-9 * float(g["flow_abs_sum"])
+    assert iw.shape == (B, 2, 256, 256) and ifm.shape == (B, 1, 256, 256) and set(np.unique(g["if_mask"] >= 0)) == {True}
+
+
+@pytest.mark.parametrize("cfg", [(16, 2, 4, "batch"), (32, 1, 5, "batch"), (16, 4, 3, "instance"), (64, 2, 4, "instance")])
+def test_host_module_has_the_reference_checkpoint_layout(cfg):
+    nf, ss, ns, norm = cfg
+    net = FlowUnet(136, nf=nf, start_scale=ss, num_scale=ns, norm=norm)
+    keys = [(k, tuple(v.shape)) for k, v in net.state_dict().items() if not k.endswith("num_batches_tracked")]
+    assert keys == FO.state_dict_spec(136, nf, ss, ns, norm)
+    net.load_state_dict(FO.make_state_dict(136, nf, ss, ns, norm), strict=False)
+
+
+def test_refuses_cpu_tensors_training_mode_and_inconsistent_pyramids():
+    net = FlowUnet(136, nf=8, start_scale=2, num_scale=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 136, 224, 224))
+    assert not FO.consistent(224, 2, 5) and FO.consistent(224, 2, 4) and FO.consistent(224, 1, 5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_flow_network_matches_the_oracle(name):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dev = torch.device("cuda", 0)
+    nf, ss, ns, norm, B = CASES[name]
+    sd = FO.make_state_dict(136, nf, ss, ns, norm, seed=_seed(name))
+    net = FlowUnet(136, nf=nf, start_scale=ss, num_scale=ns, norm=norm).to(dev).eval()
+    net.load_state_dict(sd, strict=False)
+    x = kp_maps(B, seed=7 + B)
+    flow, vis, _, _ = net(x.to(dev))
+    assert net.last_launch_count() >= 10   # the CUDA path ran (no fallback exists)
+    want_flow, want_vis, _, _ = FO.flow_unet_forward(sd, x, nf, ss, ns, norm)
+    ef, ev = (flow.cpu() - want_flow).abs().max().item(), (vis.cpu() - want_vis).abs().max().item()
+    scale = max(1.0, want_flow.abs().max().item(), want_vis.abs().max().item())
+    assert ef <= 1e-3 * scale and ev <= 1e-3 * scale, (ef, ev, scale)
+    # the tensors the generator consumes: equal wherever the visibility arg-max is not a near-tie
+    iw, ifm = net.warp_tensors(x.to(dev))
+    want_iw, want_ifm = FO.warp_outputs(want_flow, want_vis)
+    top2 = want_vis.topk(2, dim=1).values
+    near_tie = ((top2[:, :1] - top2[:, 1:]) < 1e-3 * scale).float()
+    frac_tie = near_tie.mean().item()
+    bad = ((ifm.cpu() - want_ifm).abs() > 1e-6).float().mean().item()
+    assert bad <= 4 * frac_tie + 1e-4, (bad, frac_tie)
+    same = (ifm.cpu() - want_ifm).abs() <= 1e-6
+    d = ((iw.cpu() - want_iw).abs() * same).max().item()
+    assert d <= 20 * 8 / 7 * 1e-3 * scale + 1e-4, d
+    # run-to-run and batch-vs-single determinism
+    flow2, vis2, _, _ = net(x.to(dev))
+    assert torch.equal(flow, flow2) and torch.equal(vis, vis2)
+    one, _, _, _ = net(x[:1].to(dev))
+    assert torch.equal(one, flow[:1])
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_flow_network_warp_from_landmarks():
+    """geomcgt_ifw_test_model.py:62-76 end to end: landmarks -> key-point maps (GPU) -> netF -> iw_flow / mask."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dev = torch.device("cuda", 0)
+    nf, ss, ns, norm = 16, 2, 4, "batch"
+    sd = FO.make_state_dict(136, nf, ss, ns, norm, seed=5)
+    net = FlowUnet(136, nf=nf, start_scale=ss, num_scale=ns, norm=norm).to(dev).eval()
+    net.load_state_dict(sd, strict=False)
+    src, seq = OC.landmark_sequence(3, seed=11)
+    lm1 = torch.from_numpy(np.repeat(src[None], 3, 0))
+    lm2 = torch.from_numpy(seq)
+    iw, ifm = flow_network_warp(net, None, lm1.to(dev), lm2.to(dev))
+    x = torch.from_numpy(np.concatenate([OC.kp_to_map(lm1.numpy() * 7 / 8), OC.kp_to_map(lm2.numpy() * 7 / 8)], 1))
+    want_iw, want_ifm = FO.warp_outputs(*FO.flow_unet_forward(sd, x, nf, ss, ns, norm)[:2])
+    same = (ifm.cpu() - want_ifm).abs() <= 1e-6
+    assert same.float().mean().item() >= 0.999
+    assert ((iw.cpu() - want_iw).abs() * same).max().item() <= 0.05
+    assert iw.shape == (3, 2, 256, 256) and ifm.shape == (3, 1, 256, 256)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_clip_renderer_makes_its_own_flow_with_netF():
+    """ClipRenderer(netF=...) == ClipRenderer fed with flow_network_warp's tensors (the reference's set_input + forward)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import animateportrait_b200 as ap
+    from animateportrait_b200 import synth
+    from animateportrait_b200.clip import ClipRenderer
+    dev = torch.device("cuda", 0)
+    T = 5
+    netF = FlowUnet(136, nf=16, start_scale=2, num_scale=4, norm="batch").to(dev).eval()
+    netF.load_state_dict(FO.make_state_dict(136, 16, 2, 4, "batch", seed=2, gain=0.08), strict=False)
+    net = ap.define_G(3, 1, 64, ap.NETG_NAME, "instance", False, "normal", 0.02, [0], div=3, disp=3)
+    net.module.load_state_dict(synth.make_state_dict(1, seed=3, bias_std=0.3))
+    photo, matte, static, src, seq, _, _ = synth.make_clip(T, output_nc=1, seed=33)
+    r = ClipRenderer(net, batch=2, netF=netF)
+    r.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
+    got = r.render(seq.to(dev))
+    iw, ifm = flow_network_warp(netF, None, src.to(dev)[None].expand(T, -1, -1), seq.to(dev))
+    assert 0.0 < ifm.mean().item() and iw.abs().max().item() > 0.0
+    want = ClipRenderer(net, batch=2)
+    want.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
+    assert torch.equal(got, want.render(seq.to(dev), iw, ifm))

@@ -4,7 +4,7 @@
 set -e
 NAME=$1; EXTRA=$2
 mkdir -p ab/obj_$NAME
-for f in netg conv_umma conv_halo conv_stem conv_out landmark conv_simt elementwise compose conditioning; do
+for f in netg conv_umma conv_halo conv_stem conv_out landmark conv_simt elementwise compose conditioning flownet; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr $EXTRA \
     -c animateportrait_b200/csrc/$f.cu -o ab/obj_$NAME/$f.o &
 done
