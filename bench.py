@@ -203,7 +203,7 @@ def run_reference(args, rank):
 
 CLIP_METRIC_NOTE = ("configs[2]: one photo + {T} target landmark sets (12 s clip), landmark maps + Delaunay motion field on the "
                     "GPU, netG output_nc={onc} precision={prec} in batches of {B}{share}, blend with the static drawing, uint8 frames; "
-                    "intrinsic flow / visibility mask are device-resident stand-ins for netF's output (not built)")
+                    "intrinsic flow / visibility mask: {flow}")
 
 
 def _cpu_clip_frames(fwd, clip, frames):
@@ -265,7 +265,7 @@ def run_reference_clip(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CLIP_METRIC_NOTE.format(T=args.frames, onc=args.output_nc, prec="fp32 (CPU)", B=1, share="")
+            "config": {"workload": CLIP_METRIC_NOTE.format(T=args.frames, onc=args.output_nc, prec="fp32 (CPU)", B=1, share="", flow="device-resident stand-ins for netF's output")
                        + f"; step = {n}-frame sample of the clip"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -300,7 +300,18 @@ def run_clip(args, rank, local_rank, world):
     flow_d, ifm_d = flow[lo:hi].to(dev), ifmask[lo:hi].to(dev)
     seq_host = seq.pin_memory()
     seq_dev = seq.to(dev) if rank == 0 else None
-    r = ClipRenderer(net, batch=B, share_photo=not args.no_share_photo)
+    netF = None
+    if args.flow_net:
+        # row f3: netF makes iw_flow / if_mask per batch from the landmarks instead of the device-resident stand-ins.  The
+        # released configuration is unknown (train_opt.json does not ship): "nf,start_scale,num_scale,norm", seeded weights
+        from animateportrait_b200.flownet import FlowUnet
+        nf_, ss_, ns_, norm_ = args.flow_net.split(",")
+        netF = FlowUnet(136, nf=int(nf_), start_scale=int(ss_), num_scale=int(ns_), norm=norm_).to(dev).eval()
+        g_ = torch.Generator().manual_seed(0)
+        with torch.no_grad():
+            for p_ in netF.parameters():
+                p_.copy_(torch.randn(p_.shape, generator=g_) * 0.05)
+    r = ClipRenderer(net, batch=B, share_photo=not args.no_share_photo, netF=netF)
     r.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
     mine = torch.empty((hi - lo, 256, 256, 3), dtype=torch.uint8, device=dev)
     frames_host = torch.empty((T, 256, 256, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
@@ -313,7 +324,10 @@ def run_clip(args, rank, local_rank, world):
     def one_pass(lm_rank0):
         lm = _scatter(lm_rank0, (68, 2), T, dev, None) if world > 1 else lm_rank0
         if hi > lo:
-            r.render(lm, flow_d, ifm_d, out=mine)
+            if netF is not None:
+                r.render(lm, out=mine)
+            else:
+                r.render(lm, flow_d, ifm_d, out=mine)
         return _gather(mine, T, None) if world > 1 else mine
 
     # ---------------- device-resident: landmarks already in HBM, frames stay in HBM ----------------
@@ -375,6 +389,15 @@ def run_clip(args, rank, local_rank, world):
         ev[2].record()
     torch.cuda.synchronize()
     cond_ms = {"draw2": ev[0].elapsed_time(ev[1]), "cal_motion256": ev[1].elapsed_time(ev[2])}
+    if netF is not None:
+        from animateportrait_b200.flownet import flow_network_warp
+        lm1_b = src.to(dev)[None].expand(nb, -1, -1)
+        for _ in range(2):
+            ev[0].record()
+            flow_network_warp(netF, None, lm1_b, lm_b)
+            ev[1].record()
+        torch.cuda.synchronize()
+        cond_ms["netF_flow_network_warp"] = ev[0].elapsed_time(ev[1])
     photo_b, land1_b = r._expanded(nb)[:2]
     land2_b = cond.draw2(256, 256, lm_b, 3)
     net.set_profiling(True)
@@ -427,7 +450,10 @@ def run_clip(args, rank, local_rank, world):
                 "data": "synthetic",
                 "config": {"workload": CLIP_METRIC_NOTE.format(T=T, onc=onc, prec=args.precision, B=B,
                                                                share=" (photo-only encoder layers once per batch)"
-                                                               if not args.no_share_photo else " (B copies of the photo)"),
+                                                               if not args.no_share_photo else " (B copies of the photo)",
+                                                               flow=(f"netF FlowUnet({args.flow_net}) per batch, seeded weights"
+                                                                     if args.flow_net else
+                                                                     "device-resident stand-ins for netF's output")),
                            "l2": f"every batch touches a {net.workspace_bytes(min(B, T)) / 1e9:.1f} GB working set (> 126 MB L2); "
                                  "per-frame inputs differ for every frame of the clip",
                            "parallelism": f"dp{world} (frames of one clip sharded; landmark scatter + frame gather only)"},
@@ -460,6 +486,8 @@ def main():
                      help="N > 1: frames per GPU of the clip rank 0 owns (BASELINE.json configs[3]: 64)")
     ap_.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
                      help="N > 1: how the frames return to rank 0 (frames.render_frames_sharded)")
+    ap_.add_argument("--flow-net", default=None, dest="flow_net",
+                     help="clip workload: run netF (row f3) per batch, e.g. 32,2,4,batch = nf,start_scale,num_scale,norm")
     ap_.add_argument("--no-share-photo", action="store_true",
                      help="clip workload: hand netG B copies of the photo instead of the shared-photo entry point")
     args = ap_.parse_args()

@@ -51,7 +51,9 @@ def test_define_g_signature_matches_reference():
     assert params[:15] == ["input_nc", "output_nc", "ngf", "netG", "norm", "use_dropout", "init_type", "init_gain",
                            "gpu_ids", "model0_res", "model1_res", "extra_channel", "div", "disp", "regarch"]
     fwd = list(inspect.signature(ap.ResnetConditionTriGenerator32_full_ifw.forward).parameters)
-    assert fwd == ["self", "input", "land1", "land2", "motion", "flow", "ifmask"]
+    # the reference's six positional tensors (networks.py:1315); `out=` is a keyword-only-in-practice extension with a default
+    assert fwd[:7] == ["self", "input", "land1", "land2", "motion", "flow", "ifmask"] and fwd[7:] == ["out"]
+    assert inspect.signature(ap.ResnetConditionTriGenerator32_full_ifw.forward).parameters["out"].default is None
 
 
 def test_unsupported_configurations_raise_like_the_reference():
@@ -138,3 +140,30 @@ def test_sitecustomize_shim_swaps_the_class_inside_the_reference_define_G():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "animateportrait_b200", "shim"), root]))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=REF_MODULE2, timeout=300)
     assert "SHIM_OK 74" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
+
+
+def test_native_handle_is_never_shared_with_replicas_or_copies():
+    """nn.DataParallel.replicate copies the module's __dict__ and copy.deepcopy cannot carry a ctypes pointer: every such
+    copy must start without a native handle (and create its own on first use) instead of sharing -- and later freeing --
+    the original's."""
+    import copy
+    net = ap.ResnetConditionTriGenerator32_full_ifw(3, 1, 64, norm_layer=ap.get_norm_layer("instance"), n_blocks=9, div=3, disp=3)
+    net._handle = 1234            # stands in for a live ap_netg*
+    net._handle_device = 0
+    rep = net._replicate_for_data_parallel()
+    assert rep._handle is None and rep._handle_owner == id(rep) and net._handle == 1234
+    for c in (copy.copy(net), copy.deepcopy(net)):
+        assert c._handle is None and c._handle_owner == id(c) and c._dirty
+    assert len(dict(rep._weight_tensors())) == 0 or len(dict(rep._weight_tensors())) == 74
+    assert sorted(dict(net._weight_tensors())) == sorted(net.state_dict())
+    net._handle = None
+
+
+def test_in_place_weight_changes_are_seen_without_a_hint():
+    net = ap.ResnetConditionTriGenerator32_full_ifw(3, 1, 64, norm_layer=ap.get_norm_layer("instance"), n_blocks=9, div=3, disp=3)
+    a = net._weights_signature()
+    with torch.no_grad():
+        net.model3[7].bias.add_(1.0)
+    b = net._weights_signature()
+    net.load_state_dict(net.state_dict())
+    assert a != b and net._weights_signature() != b
