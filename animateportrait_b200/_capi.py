@@ -24,6 +24,8 @@ SYMBOLS = {
     "ap_netg_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
     "ap_netg_forward": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
     "ap_netg_forward_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "ap_netg_forward_host_async": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "ap_netg_host_sync": (C.c_int, [C.c_void_p]),
     "ap_netg_forward_shared_photo": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
     "ap_netg_compose": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7),
     "ap_netg_last_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

@@ -48,13 +48,18 @@ struct alignas(64) HaloParams {
   stat_t* stats;
   int stat_C, stat_coff;
   int n_full, split, n_items;
+  // W ring: `nw` slots of `wslot` bytes.  Sized per launch from the widest item: when every item is an N-split part
+  // (small batches) the same shared memory holds up to 8 short stages instead of 2-4 long ones -- at batch size 1 the
+  // conv is bound by the latency of its 36 (tap, chunk) stages, not by bytes
+  int nw, wslot;
 };
 
 template <int NPROD, int CG>
 struct HaloCfg {
   static constexpr int PLANES = NPROD == 3 ? 2 : 1;
   static constexpr int NA = (NPROD == 1 && CG == 2) ? 3 : 2;                    // A patches in flight
-  static constexpr int NW = NPROD == 3 ? 2 : (CG == 2 ? 4 : 3);                 // W stages
+  static constexpr int NW = NPROD == 3 ? 2 : (CG == 2 ? 4 : 3);                 // W stages of full-width items
+  static constexpr int NW_MAX = 8;
   static constexpr int W_ROWS = 256 / CG;
   static constexpr int W_TILE = W_ROWS * 128;
   static constexpr int A_STAGE = PLANES * H_A_PLANE;
@@ -103,20 +108,21 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr) {
 template <int NPROD, int CG>
 __global__ void __launch_bounds__(224, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<NPROD, CG>;
-  constexpr int PLANES = Cfg::PLANES, NA = Cfg::NA, NW = Cfg::NW;
+  constexpr int PLANES = Cfg::PLANES, NA = Cfg::NA;
+  const int NW = p.nw;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t sA = smem_base;
   const uint32_t sW = smem_base + NA * Cfg::A_STAGE;
-  const uint32_t epi_s = sW + NW * Cfg::W_STAGE;
-  uint8_t* epi_gen = smem_gen + NA * Cfg::A_STAGE + NW * Cfg::W_STAGE;
+  const uint32_t epi_s = sW + Cfg::NW * Cfg::W_STAGE;
+  uint8_t* epi_gen = smem_gen + NA * Cfg::A_STAGE + Cfg::NW * Cfg::W_STAGE;
   constexpr int EPI_SLABS = Cfg::EPI_SLABS;
   const uint32_t bars = epi_s + Cfg::EPI_BYTES;
-  // barriers: a_full +0, a_empty +24, w_full +48, w_empty +80, tfull +112, tempty +128, tmem pointer +144
-  const uint32_t b_afull = bars, b_aempty = bars + 24, b_wfull = bars + 48, b_wempty = bars + 80, b_tfull = bars + 112,
-                 b_tempty = bars + 128;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + Cfg::EPI_BYTES + 144);
+  // barriers: a_full +0, a_empty +24, w_full +48, w_empty +112, tfull +176, tempty +192, tmem pointer +208
+  const uint32_t b_afull = bars, b_aempty = bars + 24, b_wfull = bars + 48, b_wempty = bars + 112, b_tfull = bars + 176,
+                 b_tempty = bars + 192;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_gen + Cfg::EPI_BYTES + 208);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
@@ -202,11 +208,11 @@ __global__ void __launch_bounds__(224, 1) conv_halo_kernel(const __grid_constant
             const uint32_t s = cnt % NW, ph = (cnt / NW) & 1u;
             mbar_wait(b_wempty + 8 * s, ph ^ 1u);
             if (rank == 0) mbar_expect_tx(b_wfull + 8 * s, CG * tx_bytes);
-            const uint32_t dst = sW + s * Cfg::W_STAGE;
+            const uint32_t dst = sW + s * p.wslot;
             for (int b = 0; b < nbox; ++b) {
 #pragma unroll
               for (int pl = 0; pl < PLANES; ++pl) {
-                const uint32_t d = dst + pl * Cfg::W_TILE + b * 8192;
+                const uint32_t d = dst + pl * (p.wslot / PLANES) + b * 8192;
                 if (CG == 2) tma_load_3d_pair(d, &mW[pl], wfull0 + 8 * s, ch * 64, wrow0 + 64 * b, p.slab[t]);
                 else tma_load_3d(d, &mW[pl], wfull0 + 8 * s, ch * 64, wrow0 + 64 * b, p.slab[t]);
               }
@@ -242,12 +248,12 @@ __global__ void __launch_bounds__(224, 1) conv_halo_kernel(const __grid_constant
             mbar_wait(b_wfull + 8 * ws, wph);
             tc_fence_after();
             const uint32_t va = pa + (uint32_t)((p.ty[t] * H_BOX_W + p.tx[t]) * 128);
-            const uint32_t vw = sW + ws * Cfg::W_STAGE;
+            const uint32_t vw = sW + ws * p.wslot;
             const uint64_t a_hi = make_halo_desc(va);
             const uint64_t w_hi = make_sw128_desc(vw);
             if (NPROD == 3) {
               const uint64_t a_lo = make_halo_desc(va + H_A_PLANE);
-              const uint64_t w_lo = make_sw128_desc(vw + Cfg::W_TILE);
+              const uint64_t w_lo = make_sw128_desc(vw + p.wslot / PLANES);
               for (int k = 0; k < ksteps; ++k) {
                 const uint64_t o = (uint64_t)(k * 2);
                 if (CG == 2) {
@@ -380,7 +386,10 @@ int halo_init_device() {  // called by umma_init for every device it sees (under
   return AP_OK;
 }
 
-// 0: tap-shifted kernel everywhere; bit 0: halo kernel for the single-product (bf16) trunk; bit 1: for the 3-product trunk
+// AP_NETG_HALO: 0 = tap-shifted kernel everywhere; bit 0: halo kernel for the single-product (bf16) trunk; bit 1: for the
+// 3-product trunk as well (tensor-bound: measured 3 % slower than the tap-shifted pair kernel at B = 16 and no faster at
+// B = 1, where 432 narrow MMAs per item bound the conv, not bytes).  Default 1.  The choice never depends on the batch
+// size: a frame must come out bit-identical whether it is rendered alone or in a batch.
 static int halo_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("AP_NETG_HALO"); v = e ? atoi(e) : 1; }
@@ -393,7 +402,8 @@ static int halo_cg_pref() {  // AP_HALO_CG: 1 or 2 for the single-product kernel
 }
 
 bool halo_conv_eligible(const ConvGeom& g, const Act& in, int nprod, bool packed) {
-  if (packed || !(halo_mode() & (nprod == 3 ? 2 : 1))) return false;
+  if (packed) return false;
+  if (!(halo_mode() & (nprod == 3 ? 2 : 1))) return false;
   if (g.stride != 1 || g.os != 1 || g.Hv != 64 || g.Wv != 64 || g.Cout != 256 || g.taps.n != 9) return false;
   if (in.H != 64 || in.W != 64) return false;
   int dev = 0;
@@ -466,6 +476,14 @@ int halo_conv_create(HaloConv** out, const ConvGeom& g, const Act& in, int in_co
   p.split = split;
   p.n_full = groups - rem;
   p.n_items = p.n_full + rem * split;
+  {
+    const int planes = nprod == 3 ? 2 : 1;
+    const int nw_full = nprod == 3 ? 2 : (c->cg == 2 ? 4 : 3);
+    const int ring = nw_full * planes * wrows * 128;
+    const int widest = p.n_full > 0 ? wrows : wrows / split;       // W rows per CTA of the widest item of this launch
+    p.wslot = planes * widest * 128;                               // multiple of 1024 (widest >= 32 rows, planes x 4 KB)
+    p.nw = ring / p.wslot < 8 ? ring / p.wslot : 8;
+  }
   c->grid = dim3((unsigned)((p.n_items < G ? p.n_items : G) * c->cg), 1);
   *out = c;
   return AP_OK;

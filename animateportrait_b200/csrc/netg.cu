@@ -105,10 +105,18 @@ struct Plan {
   std::vector<UmmaConv*> convs;
   std::map<std::string, TapRec> taps;
   // staging for ap_netg_forward_host
-  float* h_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float* h_out = nullptr;
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_in[3] = {nullptr, nullptr, nullptr};
+  // two slots: while the forward of one host call computes, the inputs of the next call upload into the other slot and
+  // the frames of the previous one download (ap_netg_forward_host_async)
+  struct HostSlot {
+    float* h_in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* h_out = nullptr;
+    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_computed = nullptr, ev_done = nullptr;
+    bool busy = false;
+  };
+  HostSlot hs[2];
+  uint64_t host_calls = 0;
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
   // independent branches of the graph (encoder branches, landmark branch, ResnetBlock2 shortcuts) run on side
   // streams so that HBM-bound kernels overlap the tensor-bound persistent convs; fork/join events by index
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
@@ -122,11 +130,15 @@ struct Plan {
     if (d_io) cudaFree(d_io);
     if (arena) cudaFree(arena);
     if (sarena) cudaFree(sarena);
-    for (float* p : h_in) if (p) cudaFree(p);
-    if (h_out) cudaFree(h_out);
+    for (HostSlot& sl : hs) {
+      for (float* p : sl.h_in) if (p) cudaFree(p);
+      if (sl.h_out) cudaFree(sl.h_out);
+      for (cudaEvent_t e : sl.ev_in) if (e) cudaEventDestroy(e);
+      if (sl.ev_computed) cudaEventDestroy(sl.ev_computed);
+      if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    if (ev_start) cudaEventDestroy(ev_start);
-    for (cudaEvent_t e : ev_in) if (e) cudaEventDestroy(e);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
   }
 };
 
@@ -980,6 +992,43 @@ int ap_netg_forward_shared_photo(ap_netg* h, int B, const float* input, const fl
   return forward_impl(h, B, in, (cudaStream_t)cuda_stream, nullptr, true);
 }
 
+// Host-buffer call into staging slot `slot`: uploads on the copy stream in the order the forward consumes them (photo ->
+// stems, motion/flow/ifmask -> warps, landmarks -> landmark branch; the compute stream waits per group), forward on `st`,
+// download of the frames on a second copy stream.  Returns without waiting; slot.ev_done marks the frames' arrival.
+static int host_enqueue(ap_netg* h, Plan* pl, int B, const float* const src[6], float* out, cudaStream_t st, int slot) {
+  const size_t px = (size_t)B * 256 * 256;
+  const size_t sz[6] = {px * 3, px, px, px * 2, px * 2, px};
+  if (!pl->copy_stream) {
+    AP_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    AP_CUDA(cudaStreamCreateWithFlags(&pl->d2h_stream, cudaStreamNonBlocking));
+  }
+  Plan::HostSlot& sl = pl->hs[slot];
+  if (!sl.h_out) {
+    for (int i = 0; i < 3; ++i) AP_CUDA(cudaEventCreateWithFlags(&sl.ev_in[i], cudaEventDisableTiming));
+    AP_CUDA(cudaEventCreateWithFlags(&sl.ev_computed, cudaEventDisableTiming));
+    AP_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < 6; ++i) AP_CUDA(cudaMalloc(&sl.h_in[i], sz[i] * sizeof(float)));
+    AP_CUDA(cudaMalloc(&sl.h_out, px * h->onc * sizeof(float)));
+  }
+  if (sl.busy) AP_CUDA(cudaEventSynchronize(sl.ev_done));  // the call that used this slot two calls ago has fully drained
+  sl.busy = true;
+  const int order[6] = {0, 3, 4, 5, 1, 2};
+  for (int k = 0; k < 6; ++k) {
+    const int i = order[k];
+    AP_CUDA(cudaMemcpyAsync(sl.h_in[i], src[i], sz[i] * sizeof(float), cudaMemcpyHostToDevice, pl->copy_stream));
+    if (k == 0) AP_CUDA(cudaEventRecord(sl.ev_in[0], pl->copy_stream));
+    if (k == 3) AP_CUDA(cudaEventRecord(sl.ev_in[1], pl->copy_stream));
+    if (k == 5) AP_CUDA(cudaEventRecord(sl.ev_in[2], pl->copy_stream));
+  }
+  Inputs in{sl.h_in[0], sl.h_in[1], sl.h_in[2], sl.h_in[3], sl.h_in[4], sl.h_in[5], sl.h_out};
+  AP_TRY(forward_impl(h, B, in, st, sl.ev_in));
+  AP_CUDA(cudaEventRecord(sl.ev_computed, st));
+  AP_CUDA(cudaStreamWaitEvent(pl->d2h_stream, sl.ev_computed, 0));
+  AP_CUDA(cudaMemcpyAsync(out, sl.h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, pl->d2h_stream));
+  AP_CUDA(cudaEventRecord(sl.ev_done, pl->d2h_stream));
+  return AP_OK;
+}
+
 int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* land1, const float* land2,
                          const float* motion, const float* flow, const float* ifmask, float* out, void* cuda_stream) {
   AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
@@ -988,43 +1037,56 @@ int ap_netg_forward_host(ap_netg* h, int B, const float* input, const float* lan
   Plan* pl = nullptr;
   AP_TRY(get_plan(h, B, false, &pl));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const size_t px = (size_t)B * 256 * 256;
-  const size_t sz[6] = {px * 3, px, px, px * 2, px * 2, px};
   const float* src[6] = {input, land1, land2, motion, flow, ifmask};
-  if (!pl->copy_stream) {
-    AP_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
-    AP_CUDA(cudaEventCreateWithFlags(&pl->ev_start, cudaEventDisableTiming));
-    for (int i = 0; i < 3; ++i) AP_CUDA(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
-    for (int i = 0; i < 6; ++i) AP_CUDA(cudaMalloc(&pl->h_in[i], sz[i] * sizeof(float)));
-    AP_CUDA(cudaMalloc(&pl->h_out, px * h->onc * sizeof(float)));
-  }
-  // The six uploads run on a side stream in the order the forward consumes them (photo -> stems,
-  // motion/flow/ifmask -> warps, landmarks -> landmark branch); the compute stream waits per group, so only
-  // the photo upload is exposed and the rest hides behind the stem / encoder kernels.
-  Inputs in{pl->h_in[0], pl->h_in[1], pl->h_in[2], pl->h_in[3], pl->h_in[4], pl->h_in[5], pl->h_out};
-  const int order[6] = {0, 3, 4, 5, 1, 2};
   if (h->graphs && !h->profiling && h->prec != AP_PREC_FP32_SIMT && B <= 4) {
     // small batches (the reference's own call is batch size 1, Module2/test.py:42): the uploads are tens of
     // microseconds, launch overhead is what matters -- copy in stream order and replay the plan's CUDA graph
+    const size_t px = (size_t)B * 256 * 256;
+    const size_t sz[6] = {px * 3, px, px, px * 2, px * 2, px};
+    Plan::HostSlot& sl = pl->hs[0];
+    if (sl.busy) AP_CUDA(cudaEventSynchronize(sl.ev_done));
+    if (!sl.h_out) {
+      for (int i = 0; i < 3; ++i) AP_CUDA(cudaEventCreateWithFlags(&sl.ev_in[i], cudaEventDisableTiming));
+      AP_CUDA(cudaEventCreateWithFlags(&sl.ev_computed, cudaEventDisableTiming));
+      AP_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+      for (int i = 0; i < 6; ++i) AP_CUDA(cudaMalloc(&sl.h_in[i], sz[i] * sizeof(float)));
+      AP_CUDA(cudaMalloc(&sl.h_out, px * h->onc * sizeof(float)));
+    }
+    const int order[6] = {0, 3, 4, 5, 1, 2};
     for (int k = 0; k < 6; ++k)
-      AP_CUDA(cudaMemcpyAsync(pl->h_in[order[k]], src[order[k]], sz[order[k]] * sizeof(float), cudaMemcpyHostToDevice, st));
+      AP_CUDA(cudaMemcpyAsync(sl.h_in[order[k]], src[order[k]], sz[order[k]] * sizeof(float), cudaMemcpyHostToDevice, st));
+    Inputs in{sl.h_in[0], sl.h_in[1], sl.h_in[2], sl.h_in[3], sl.h_in[4], sl.h_in[5], sl.h_out};
     AP_TRY(forward_impl(h, B, in, st, nullptr));
-    AP_CUDA(cudaMemcpyAsync(out, pl->h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    AP_CUDA(cudaMemcpyAsync(out, sl.h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, st));
     AP_CUDA(cudaStreamSynchronize(st));
     return AP_OK;
   }
-  AP_CUDA(cudaEventRecord(pl->ev_start, st));
-  AP_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->ev_start, 0));
-  for (int k = 0; k < 6; ++k) {
-    const int i = order[k];
-    AP_CUDA(cudaMemcpyAsync(pl->h_in[i], src[i], sz[i] * sizeof(float), cudaMemcpyHostToDevice, pl->copy_stream));
-    if (k == 0) AP_CUDA(cudaEventRecord(pl->ev_in[0], pl->copy_stream));
-    if (k == 3) AP_CUDA(cudaEventRecord(pl->ev_in[1], pl->copy_stream));
-    if (k == 5) AP_CUDA(cudaEventRecord(pl->ev_in[2], pl->copy_stream));
-  }
-  AP_TRY(forward_impl(h, B, in, st, pl->ev_in));
-  AP_CUDA(cudaMemcpyAsync(out, pl->h_out, px * h->onc * sizeof(float), cudaMemcpyDeviceToHost, st));
-  AP_CUDA(cudaStreamSynchronize(st));
+  AP_TRY(host_enqueue(h, pl, B, src, out, st, 0));
+  AP_CUDA(cudaEventSynchronize(pl->hs[0].ev_done));
+  pl->hs[0].busy = false;
+  return AP_OK;
+}
+
+int ap_netg_forward_host_async(ap_netg* h, int B, const float* input, const float* land1, const float* land2,
+                               const float* motion, const float* flow, const float* ifmask, float* out, void* cuda_stream) {
+  AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1 && input && land1 && land2 && motion && flow && ifmask && out, AP_ERR_INVALID, "bad argument");
+  AP_CUDA(cudaSetDevice(h->device));
+  Plan* pl = nullptr;
+  AP_TRY(get_plan(h, B, false, &pl));
+  const float* src[6] = {input, land1, land2, motion, flow, ifmask};
+  return host_enqueue(h, pl, B, src, out, (cudaStream_t)cuda_stream, (int)(pl->host_calls++ & 1));
+}
+
+int ap_netg_host_sync(ap_netg* h) {
+  AP_REQUIRE(h != nullptr, AP_ERR_INVALID, "null handle");
+  AP_CUDA(cudaSetDevice(h->device));
+  for (auto& kv : h->plans)
+    for (Plan::HostSlot& sl : kv.second->hs)
+      if (sl.busy) {
+        AP_CUDA(cudaEventSynchronize(sl.ev_done));
+        sl.busy = false;
+      }
   return AP_OK;
 }
 

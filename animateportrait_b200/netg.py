@@ -307,6 +307,36 @@ class ResnetConditionTriGenerator32_full_ifw(nn.Module):
                         "ap_netg_forward_host")
         return out
 
+    @torch.no_grad()
+    def forward_host_async(self, input, land1, land2, motion, flow, ifmask, out: torch.Tensor,
+                           device: Optional[torch.device] = None) -> torch.Tensor:
+        """Pipelined forward_host (`ap_netg_forward_host_async`): returns at once; up to two calls are in flight, the
+        uploads of one overlapping the forward of the other.  Keep the (pinned) host tensors alive and do not read `out`
+        before host_sync()."""
+        dev = torch.device(device if device is not None else next(self.parameters()).device)
+        if dev.type != "cuda":
+            raise RuntimeError("forward_host_async needs the module's parameters (or `device`) on a CUDA device")
+        B = input.shape[0]
+        ts = [t.detach().to(dtype=torch.float32).contiguous() for t in (input, land1, land2, motion, flow, ifmask)]
+        if any(t.is_cuda for t in ts) or out.is_cuda:
+            raise RuntimeError("forward_host_async takes host tensors")
+        if tuple(out.shape) != (B, self.output_nc, 256, 256) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError(f"out: expected a contiguous fp32 host tensor {(B, self.output_nc, 256, 256)}")
+        self._host_keep = getattr(self, "_host_keep", [])[-12:] + ts   # the copies read them after this call returns
+        with torch.cuda.device(dev):
+            self._sync(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib().ap_netg_forward_host_async(self._handle, B, *[C.c_void_p(t.data_ptr()) for t in ts],
+                                                               C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
+                        "ap_netg_forward_host_async")
+        return out
+
+    def host_sync(self) -> None:
+        """Waits until every forward_host_async call has delivered its frames."""
+        if self._handle is not None:
+            _capi.check(_capi.lib().ap_netg_host_sync(self._handle), "ap_netg_host_sync")
+            self._host_keep = []
+
     # ---- introspection used by tests / bench ------------------------------------------------------
     def last_launch_count(self) -> int:
         n = C.c_int64(0)

@@ -85,6 +85,16 @@ int ap_netg_forward_host(ap_netg* handle, int B, const float* input, const float
                          const float* land2, const float* motion, const float* flow, const float* ifmask,
                          float* out, void* cuda_stream);
 
+/* Pipelined form of ap_netg_forward_host for a clip rendered batch after batch (the reference's loop over frames,
+ * Module2/test.py:58-65): returns as soon as the copies and the forward are enqueued.  Two staging slots alternate, so the
+ * inputs of call k+1 upload while call k computes and the frames of call k download while call k+1 computes; a third call
+ * in flight waits for the first to drain.  The host buffers (pinned for overlap) must stay valid, and `out` unread, until
+ * ap_netg_host_sync returns.  Same frames as ap_netg_forward_host. */
+int ap_netg_forward_host_async(ap_netg* handle, int B, const float* input, const float* land1, const float* land2,
+                               const float* motion, const float* flow, const float* ifmask, float* out,
+                               void* cuda_stream);
+int ap_netg_host_sync(ap_netg* handle);
+
 /* Output stage after netG, one fused elementwise kernel (device pointers, asynchronous on `cuda_stream`).
  * Replaces: the foreground/background blend of GeomCGTIFWTestModel.forward
  *   mask1 = F.grid_sample(mask, warp_motion, align_corners=True); fake_B = ((fake_B/2+0.5)*mask1 +

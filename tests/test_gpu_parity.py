@@ -332,3 +332,20 @@ def test_handles_on_two_devices_in_one_process():
         y_dp = dp(*[t.to("cuda:0") for t in inputs]).cpu()
         y_dp2 = dp(*[t.to("cuda:0") for t in inputs]).cpu()   # replicas of the first call are gone; the original's handle is not
     assert (y_dp - ys[0]).abs().max().item() == 0 and (y_dp2 - ys[0]).abs().max().item() == 0
+
+
+def test_pipelined_host_calls_deliver_the_same_frames(dev):
+    """ap_netg_forward_host_async: two staging slots, the uploads of one call under the forward of the previous one; five
+    calls in flight order, every frame equal to the synchronous entry point's."""
+    onc, B = 1, 3
+    sd = O.make_state_dict(onc, seed=4, bias_std=0.1)
+    net = _net(onc, sd, dev, "fp32").module
+    sets = [[t.pin_memory() for t in O.make_inputs(B, seed=300 + i, kind="smooth")] for i in range(5)]
+    want = [net.forward_host(*s_).clone() for s_ in sets]
+    outs = [torch.empty((B, onc, 256, 256), dtype=torch.float32).pin_memory() for _ in sets]
+    for s_, o in zip(sets, outs):
+        net.forward_host_async(*s_, out=o)
+    net.host_sync()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
+    assert (want[0] - want[1]).abs().max().item() > 1e-3
