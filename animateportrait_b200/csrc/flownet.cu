@@ -52,6 +52,8 @@ struct FConvP {
   int B, Hin, Win, Cin, Hv, Wv, stride, Cout, CoutP;
   int os, Hout, Wout;
   int nphase, ntaps;   // blockIdx.z = phase: output pixel (y*os + py, x*os + px)
+  const int* gate_area;  // sparse-operand gate (first conv): image n is left to fconv_sparse_kernel when gate_area[n] <= gate_thresh
+  int gate_thresh;
   int8_t py[4], px[4];
   FTap taps[4][49];
 };
@@ -73,6 +75,12 @@ __global__ void __launch_bounds__(256) fconv_kernel(const __grid_constant__ FCon
   const int tx = tid & 15, ty = tid >> 4;
   const int Ktot = p.ntaps * p.Cin;
   const FTap* taps = p.taps[ph];
+  if (p.gate_area) {  // every image this tile touches went to the sparse kernel: nothing to do
+    const int ia = m0 / HW, ib = min(m0 + 63, M - 1) / HW;
+    bool any = false;
+    for (int i = ia; i <= ib; ++i) any |= p.gate_area[i] > p.gate_thresh;
+    if (!any) return;
+  }
 
   float acc[4][4];
 #pragma unroll
@@ -138,6 +146,7 @@ __global__ void __launch_bounds__(256) fconv_kernel(const __grid_constant__ FCon
     const int mm = m0 + ty * 4 + i;
     if (mm >= M) continue;
     const int im = mm / HW, pm = mm - im * HW;
+    if (p.gate_area && p.gate_area[im] <= p.gate_thresh) continue;
     const int y = pm / p.Wv, x = pm - y * p.Wv;
     const int oy = y * p.os + p.py[ph], ox = x * p.os + p.px[ph];
     float* dst = p.out + ((size_t)(im * p.Hout + oy) * p.Wout + ox) * p.out_C + p.out_coff;
@@ -147,6 +156,257 @@ __global__ void __launch_bounds__(256) fconv_kernel(const __grid_constant__ FCon
       if (n < p.Cout) dst[n] = acc[i][j] + (p.bias ? p.bias[n] : 0.f);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register-tiled version of the same implicit GEMM for NHWC operands with Cin % 16 == 0 (every layer but the first):
+// 128 pixels x BN output channels per CTA, 8 x (BN/16) accumulators per thread, K walked in 16-channel steps that never
+// straddle a tap (so the tap geometry is per step, not per element), operands fetched as 16-byte vectors -- four threads
+// read the 64 contiguous bytes of one pixel -- and double-buffered through registers into shared memory (one barrier per
+// step).  Accumulation order per output element is k ascending, as in fconv_kernel: the results are independent of the
+// tile a pixel falls into, hence of the batch size.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FT_BM = 128, FT_BK = 16, FT_LDA = FT_BM + 4;
+
+template <int BN>
+__global__ void __launch_bounds__(256, 2) fconv_tiled_kernel(const __grid_constant__ FConvP p) {
+  constexpr int TN = BN / 16;            // columns per thread: 8 (two groups of 4), 4 or 1
+  constexpr int NBV = (FT_BK * BN / 4 + 255) / 256;  // 16-byte weight vectors per thread and step
+  __shared__ __align__(16) float As[2][FT_BK][FT_LDA];
+  __shared__ __align__(16) float Bs[2][FT_BK][BN];
+  const int tid = threadIdx.x;
+  const int HW = p.Hv * p.Wv;
+  const int M = p.B * HW;
+  const int m0 = blockIdx.x * FT_BM, n0 = blockIdx.y * BN, ph = blockIdx.z;
+  const int tx = tid & 15, ty = tid >> 4;
+  const FTap* taps = p.taps[ph];
+  const int nsteps = p.ntaps * (p.Cin / FT_BK);
+  const int steps_per_tap = p.Cin / FT_BK;
+
+  // operand loader: pixels lm0 = tid >> 2 and lm0 + 64, channel quad q = tid & 3 of the step's 16 channels
+  const int q = tid & 3;
+  int l_img[2], l_y[2], l_x[2];
+  bool l_ok[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int m = m0 + (tid >> 2) + 64 * r;
+    l_ok[r] = m < M;
+    const int mm = l_ok[r] ? m : 0;
+    l_img[r] = mm / HW;
+    const int pix = mm - l_img[r] * HW;
+    l_y[r] = pix / p.Wv;
+    l_x[r] = pix - l_y[r] * p.Wv;
+  }
+
+  float4 ra[2], rb[NBV];
+  auto fetch = [&](int step) {
+    const int t = step / steps_per_tap;
+    const int c = (step - t * steps_per_tap) * FT_BK + 4 * q;
+    const int dy = taps[t].dy, dx = taps[t].dx, slab = taps[t].slab;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int iy = l_y[r] * p.stride + dy, ix = l_x[r] * p.stride + dx;
+      if (l_ok[r] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
+        v = *reinterpret_cast<const float4*>(p.in + ((size_t)(l_img[r] * p.Hin + iy) * p.Win + ix) * p.in_C + p.in_coff + c);
+        if (p.scale) {
+          const float4 sc = *reinterpret_cast<const float4*>(p.scale + (size_t)l_img[r] * p.in_C + p.in_coff + c);
+          const float4 sh = *reinterpret_cast<const float4*>(p.shift + (size_t)l_img[r] * p.in_C + p.in_coff + c);
+          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        }
+        v.x = fact(v.x, p.act); v.y = fact(v.y, p.act); v.z = fact(v.z, p.act); v.w = fact(v.w, p.act);
+      }
+      ra[r] = v;
+    }
+    const int cb = (step - t * steps_per_tap) * FT_BK;
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int e = tid + 256 * i;               // vector index: row kk = e / (BN/4), column (e % (BN/4)) * 4
+      const int kk = e / (BN / 4), col = (e - kk * (BN / 4)) * 4;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < FT_BK && n0 + col < p.CoutP)
+        w = *reinterpret_cast<const float4*>(p.w + ((size_t)slab * p.Cin + cb + kk) * p.CoutP + n0 + col);
+      rb[i] = w;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int lm = (tid >> 2) + 64 * r;
+      As[buf][4 * q + 0][lm] = ra[r].x;
+      As[buf][4 * q + 1][lm] = ra[r].y;
+      As[buf][4 * q + 2][lm] = ra[r].z;
+      As[buf][4 * q + 3][lm] = ra[r].w;
+    }
+#pragma unroll
+    for (int i = 0; i < NBV; ++i) {
+      const int e = tid + 256 * i;
+      const int kk = e / (BN / 4), col = (e - kk * (BN / 4)) * 4;
+      if (kk < FT_BK) *reinterpret_cast<float4*>(&Bs[buf][kk][col]) = rb[i];
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int step = 0; step < nsteps; ++step) {
+    const int buf = step & 1;
+    if (step + 1 < nsteps) fetch(step + 1);
+#pragma unroll
+    for (int k = 0; k < FT_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[TN];
+      if constexpr (TN == 1) {
+        bv[0] = Bs[buf][k][tx];
+      } else {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+        if constexpr (TN == 8) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+          bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (step + 1 < nsteps) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int mm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (mm >= M) continue;
+    const int im = mm / HW, pm = mm - im * HW;
+    const int y = pm / p.Wv, x = pm - y * p.Wv;
+    const int oy = y * p.os + p.py[ph], ox = x * p.os + p.px[ph];
+    float* dst = p.out + ((size_t)(im * p.Hout + oy) * p.Wout + ox) * p.out_C + p.out_coff;
+    if constexpr (TN == 1) {
+      const int n = n0 + tx;
+      if (n < p.Cout) dst[n] = acc[i][0] + (p.bias ? p.bias[n] : 0.f);
+    } else {
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        const int n = n0 + 64 * g + tx * 4;
+        if (n + 3 < p.Cout) {
+          float4 o = make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
+          if (p.bias) { o.x += p.bias[n]; o.y += p.bias[n + 1]; o.z += p.bias[n + 2]; o.w += p.bias[n + 3]; }
+          *reinterpret_cast<float4*>(dst + n) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.Cout) dst[n + j] = acc[i][4 * g + j] + (p.bias ? p.bias[n + j] : 0.f);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The first conv of netF reads 2 x 68 key-point maps: one disc of <= 49 pixels per 224 x 224 plane, i.e. 99.9 % zeros,
+// and is 70 % of the dense network's FLOPs.  `fbbox_kernel` finds the bounding box of the non-zeros of every (image,
+// channel) plane; `fconv_sparse_kernel` gives each output pixel only the (channel, tap) pairs whose input can be non-zero.
+// A product with an exact zero contributes exactly nothing, so this is the same sum as the dense conv with the zero terms
+// left out (k ascending, taps in raster order).  Nothing is assumed about the caller's tensor: an image whose boxes cover
+// more than 1/8 of the volume stays with the dense kernel (per-image decision on the device, no host synchronisation; per
+// image so that a frame's result does not depend on its batch neighbours).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fbbox_kernel(const float* __restrict__ x, int H, int W, int C, int4* __restrict__ bbox,
+                                                    int* __restrict__ area) {
+  const int plane = blockIdx.x;  // n * C + c
+  const float* src = x + (size_t)plane * H * W;
+  int y0 = H, y1 = -1, x0 = W, x1 = -1;
+  for (int i = threadIdx.x; i < H * W; i += 256) {
+    if (src[i] != 0.f) {
+      const int yy = i / W, xx = i - yy * W;
+      y0 = min(y0, yy); y1 = max(y1, yy); x0 = min(x0, xx); x1 = max(x1, xx);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+  }
+  __shared__ int4 sb[8];
+  if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = make_int4(y0, y1, x0, x1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      y0 = min(y0, sb[k].x); y1 = max(y1, sb[k].y); x0 = min(x0, sb[k].z); x1 = max(x1, sb[k].w);
+    }
+    bbox[plane] = make_int4(y0, y1, x0, x1);  // empty plane: y1 < y0
+    if (y1 >= y0) atomicAdd(&area[plane / C], (y1 - y0 + 1) * (x1 - x0 + 1));  // integer sum: order-independent
+  }
+}
+
+struct FSparseP {
+  const float* in;     // NCHW [B,Cin,H,W]
+  const int4* bbox;    // [B*Cin]
+  const int* area;     // [B]
+  int thresh;
+  const float* w;      // [k*k][Cin][CoutP]
+  const float* bias;
+  float* out;          // NHWC [B,H,W,out_C] at channel out_coff
+  int out_C, out_coff;
+  int B, H, W, Cin, Cout, CoutP, k, pad;
+};
+constexpr int FS_MAXC = 512;
+
+// grid (tiles of 16 x 16 output pixels, groups of 16 output channels, images); a thread owns one pixel and 16 channels
+__global__ void __launch_bounds__(256) fconv_sparse_kernel(const __grid_constant__ FSparseP p) {
+  const int n = blockIdx.z;
+  if (p.area[n] > p.thresh) return;  // dense image: fconv_kernel's
+  __shared__ int4 sb[FS_MAXC];
+  for (int c = threadIdx.x; c < p.Cin; c += 256) sb[c] = p.bbox[(size_t)n * p.Cin + c];
+  __syncthreads();
+  const int tiles_x = (p.W + 15) / 16;
+  const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
+  const int y = ty0 + (threadIdx.x >> 4), x = tx0 + (threadIdx.x & 15);
+  const int cg = blockIdx.y * 16;
+  if (y >= p.H || x >= p.W) return;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  // input rows of output row y: y - pad .. y - pad + k - 1
+  const int wy0 = y - p.pad, wy1 = y - p.pad + p.k - 1, wx0 = x - p.pad, wx1 = x - p.pad + p.k - 1;
+  const int ry0 = ty0 - p.pad, ry1 = ty0 + 15 - p.pad + p.k - 1, rx0 = tx0 - p.pad, rx1 = tx0 + 15 - p.pad + p.k - 1;
+  for (int c = 0; c < p.Cin; ++c) {
+    const int4 bb = sb[c];
+    if (bb.y < ry0 || bb.x > ry1 || bb.w < rx0 || bb.z > rx1) continue;  // uniform over the CTA (covers empty planes)
+    const int ia = max(wy0, bb.x), ib = min(wy1, bb.y), ja = max(wx0, bb.z), jb = min(wx1, bb.w);
+    const float* src = p.in + ((size_t)n * p.Cin + c) * p.H * p.W;
+    for (int iy = ia; iy <= ib; ++iy)
+      for (int ix = ja; ix <= jb; ++ix) {
+        const float v = src[iy * p.W + ix];
+        if (v != 0.f) {
+          const int slab = (iy - wy0) * p.k + (ix - wx0);
+          const float* wp = p.w + ((size_t)slab * p.Cin + c) * p.CoutP + cg;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (cg + 4 * g < p.CoutP) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + 4 * g));
+              acc[4 * g + 0] = fmaf(v, w4.x, acc[4 * g + 0]);
+              acc[4 * g + 1] = fmaf(v, w4.y, acc[4 * g + 1]);
+              acc[4 * g + 2] = fmaf(v, w4.z, acc[4 * g + 2]);
+              acc[4 * g + 3] = fmaf(v, w4.w, acc[4 * g + 3]);
+            }
+        }
+      }
+  }
+  float* dst = p.out + ((size_t)(n * p.H + y) * p.W + x) * p.out_C + p.out_coff;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (cg + j < p.Cout) dst[cg + j] = acc[j] + (p.bias ? p.bias[cg + j] : 0.f);
 }
 
 // InstanceNorm2d(affine=False) of a raw NHWC plane as an operand transform: scale = rstd, shift = -mean * rstd.
@@ -302,6 +562,9 @@ struct ap_flow {
   std::vector<FBuf> cat;   // cat[l] (l >= 1): [d_{l-1} | u_l]; cat[0] = u_0
   FBuf dinner, heads;
   float *fm = nullptr, *mk = nullptr;
+  int4* bbox = nullptr;  // [B * input_nc] non-zero bounding boxes of the operand planes of the first conv
+  int* area = nullptr;   // [B] their summed areas
+  int sparse = 1, tiled = 1;  // AP_FLOW_SPARSE / AP_FLOW_TILED = 0: the one generic kernel everywhere (A/B, tests)
   int64_t last_launches = 0;
 };
 
@@ -352,6 +615,8 @@ static int flow_plan(ap_flow* h, int B) {
   const int R = 2 * h->sz[0];
   AP_TRY(flow_alloc(h, (size_t)B * 2 * R * R * 4, (void**)&h->fm));
   AP_TRY(flow_alloc(h, (size_t)B * R * R * 4, (void**)&h->mk));
+  AP_TRY(flow_alloc(h, (size_t)B * h->input_nc * sizeof(int4), (void**)&h->bbox));
+  AP_TRY(flow_alloc(h, (size_t)B * sizeof(int), (void**)&h->area));
   h->planB = B;
   return AP_OK;
 }
@@ -378,7 +643,7 @@ static void taps_convT4(FConvP* p) {
 
 static int flow_conv(ap_flow* h, int B, const float* in, int in_nchw, int in_C, int in_coff, const float* scale,
                      const float* shift, int act, int Hin, const FLayerW& w, int stride, int transposed4, int pad, float* out,
-                     int out_C, int out_coff, int Hout, cudaStream_t st) {
+                     int out_C, int out_coff, int Hout, cudaStream_t st, const int* gate_area = nullptr, int gate_thresh = 0) {
   FConvP p;
   memset(&p, 0, sizeof(p));
   p.in = in; p.in_nchw = in_nchw; p.in_C = in_C; p.in_coff = in_coff; p.scale = scale; p.shift = shift; p.act = act;
@@ -393,11 +658,41 @@ static int flow_conv(ap_flow* h, int B, const float* in, int in_nchw, int in_C, 
     p.Hv = Hout; p.Wv = Hout; p.stride = stride;
   }
   const int M = B * p.Hv * p.Wv;
-  dim3 grid((M + 63) / 64, (w.cout + 63) / 64, p.nphase);
-  fconv_kernel<<<grid, 256, 0, st>>>(p);
+  if (gate_area) { p.gate_area = gate_area; p.gate_thresh = gate_thresh; }
+  if (h->tiled && !in_nchw && !gate_area && w.cin % FT_BK == 0 && in_C % 4 == 0 && in_coff % 4 == 0 && out_C % 4 == 0 &&
+      out_coff % 4 == 0) {
+    const int mt = (M + FT_BM - 1) / FT_BM;
+    if (w.cout > 64) fconv_tiled_kernel<128><<<dim3(mt, (w.cout + 127) / 128, p.nphase), 256, 0, st>>>(p);
+    else if (w.cout > 16) fconv_tiled_kernel<64><<<dim3(mt, 1, p.nphase), 256, 0, st>>>(p);
+    else fconv_tiled_kernel<16><<<dim3(mt, 1, p.nphase), 256, 0, st>>>(p);
+  } else {
+    dim3 grid((M + 63) / 64, (w.cout + 63) / 64, p.nphase);
+    fconv_kernel<<<grid, 256, 0, st>>>(p);
+  }
   AP_CUDA(cudaGetLastError());
   launches_add(1);
   return AP_OK;
+}
+
+// The first conv on a sparse NCHW operand (stride 1): boxes of the non-zeros, the sparse kernel for the images that are
+// sparse and the generic kernel, gated per image, for those that are not.
+static int flow_conv_sparse(ap_flow* h, int B, const float* in, int Hin, const FLayerW& w, int pad, float* out, int out_C,
+                            int Hout, cudaStream_t st) {
+  AP_CUDA(cudaMemsetAsync(h->area, 0, (size_t)B * sizeof(int), st));
+  fbbox_kernel<<<B * w.cin, 256, 0, st>>>(in, Hin, Hin, w.cin, h->bbox, h->area);
+  AP_CUDA(cudaGetLastError());
+  FSparseP sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.in = in; sp.bbox = h->bbox; sp.area = h->area;
+  sp.thresh = (int)((long long)Hin * Hin * w.cin / 8);
+  sp.w = w.w; sp.bias = w.bias; sp.out = out; sp.out_C = out_C; sp.out_coff = 0;
+  sp.B = B; sp.H = Hin; sp.W = Hin; sp.Cin = w.cin; sp.Cout = w.cout; sp.CoutP = w.coutp; sp.k = w.k; sp.pad = pad;
+  const int tiles = (Hin + 15) / 16;
+  fconv_sparse_kernel<<<dim3(tiles * tiles, (w.cout + 15) / 16, B), 256, 0, st>>>(sp);
+  AP_CUDA(cudaGetLastError());
+  launches_add(2);
+  return flow_conv(h, B, in, 1, w.cin, 0, nullptr, nullptr, FACT_NONE, Hin, w, 1, 0, pad, out, out_C, 0, Hout, st, h->area,
+                   sp.thresh);
 }
 
 // operand transform of buffer channels [coff, coff + nC): the producing conv's normalisation
@@ -429,6 +724,8 @@ int ap_flow_create(ap_flow** handle, int input_nc, int nf, int start_scale, int 
   ap_flow* h = new ap_flow();
   h->input_nc = input_nc; h->nf = nf; h->start_scale = start_scale; h->num_scale = num_scale; h->norm = norm;
   h->max_nf = max_nf; h->size = size; h->device = device;
+  { const char* e = getenv("AP_FLOW_SPARSE"); if (e && e[0] == '0') h->sparse = 0; }
+  { const char* e = getenv("AP_FLOW_TILED"); if (e && e[0] == '0') h->tiled = 0; }
   int s = size, nc = nf;
   for (int sc = start_scale; sc > 1; sc /= 2) {
     s = (s + 2 - 3) / 2 + 1;
@@ -583,8 +880,12 @@ int ap_flow_forward(ap_flow* h, int B, const float* kp_maps, float* flow_out, fl
   const int64_t before = launches_get();
   const int L = h->num_scale;
   // conv_downsample: conv7x7 + norm + LeakyReLU(0.1), then 3x3 stride-2 convs (networks.py:601-612)
-  AP_TRY(flow_conv(h, B, kp_maps, 1, h->input_nc, 0, nullptr, nullptr, FACT_NONE, h->size, h->w.at("cds0"), 1, 0, 3,
-                   h->cds[0].p, h->cds[0].C, 0, h->size, st));
+  if (h->sparse && h->input_nc <= FS_MAXC && h->size == (h->size + 2 * 3 - 7) + 1) {
+    AP_TRY(flow_conv_sparse(h, B, kp_maps, h->size, h->w.at("cds0"), 3, h->cds[0].p, h->cds[0].C, h->size, st));
+  } else {
+    AP_TRY(flow_conv(h, B, kp_maps, 1, h->input_nc, 0, nullptr, nullptr, FACT_NONE, h->size, h->w.at("cds0"), 1, 0, 3,
+                     h->cds[0].p, h->cds[0].C, 0, h->size, st));
+  }
   AP_TRY(flow_norm(h, B, h->cds[0], 0, h->cds[0].C, h->w.at("cds0"), st));
   for (int i = 0; i < h->ndown; ++i) {
     const FBuf& src = h->cds[i];

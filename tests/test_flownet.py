@@ -138,3 +138,58 @@ def test_clip_renderer_makes_its_own_flow_with_netF():
     want = ClipRenderer(net, batch=2)
     want.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
     assert torch.equal(got, want.render(seq.to(dev), iw, ifm))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("cfg", [(16, 2, 4, "batch"), (8, 1, 5, "instance"), (32, 2, 4, "instance")])
+def test_sparse_and_tiled_kernels_agree_with_the_generic_kernel(cfg, monkeypatch):
+    """The default path (box-restricted first conv + register-tiled implicit GEMM, csrc/flownet.cu) against the one
+    generic kernel it replaced (AP_FLOW_SPARSE=0 AP_FLOW_TILED=0): same sums, other association."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dev = torch.device("cuda", 0)
+    nf, ss, ns, norm = cfg
+    sd = FO.make_state_dict(136, nf, ss, ns, norm, seed=21)
+    x = kp_maps(3, seed=5).to(dev)
+
+    def run():
+        net = FlowUnet(136, nf=nf, start_scale=ss, num_scale=ns, norm=norm).to(dev).eval()
+        net.load_state_dict(sd, strict=False)
+        flow, vis, _, _ = net(x)
+        return flow.cpu(), vis.cpu(), net.last_launch_count()
+
+    flow, vis, n_fast = run()
+    monkeypatch.setenv("AP_FLOW_SPARSE", "0")
+    monkeypatch.setenv("AP_FLOW_TILED", "0")
+    flow0, vis0, n_plain = run()
+    assert n_fast == n_plain + 2   # the box pass and the sparse kernel
+    scale = max(1.0, flow0.abs().max().item(), vis0.abs().max().item())
+    assert (flow - flow0).abs().max().item() <= 2e-4 * scale and (vis - vis0).abs().max().item() <= 2e-4 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_dense_operand_stays_with_the_dense_first_conv():
+    """ap_flow_forward assumes nothing about its operand: in one batch, an image of key-point discs takes the sparse
+    first conv and an image of noise the dense one (per-image decision on the device); both match the oracle, and the
+    disc image equals its own single-image result bit for bit."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dev = torch.device("cuda", 0)
+    nf, ss, ns, norm = 16, 2, 4, "instance"
+    sd = FO.make_state_dict(136, nf, ss, ns, norm, seed=9)
+    net = FlowUnet(136, nf=nf, start_scale=ss, num_scale=ns, norm=norm).to(dev).eval()
+    net.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(4)
+    x = kp_maps(3, seed=6)
+    x[1] = 0.05 * torch.randn(136, 224, 224, generator=g)
+    x[2, 7] = 0.0          # an empty plane
+    flow, vis, _, _ = net(x.to(dev))
+    want_flow, want_vis, _, _ = FO.flow_unet_forward(sd, x, nf, ss, ns, norm)
+    scale = max(1.0, want_flow.abs().max().item(), want_vis.abs().max().item())
+    assert (flow.cpu() - want_flow).abs().max().item() <= 1e-3 * scale
+    assert (vis.cpu() - want_vis).abs().max().item() <= 1e-3 * scale
+    one, _, _, _ = net(x[:1].to(dev))
+    two, _, _, _ = net(x[1:2].to(dev))
+    assert torch.equal(one, flow[:1]) and torch.equal(two, flow[1:2])

@@ -63,3 +63,48 @@ def test_output_conv_equals_channel_contraction_plus_shifted_sums():
             out += t[:, :, ky * 7 + kx, ky:ky + S, kx:kx + S]      # the 49-term shifted sum out of shared memory
     got = torch.tanh(out + bias.view(1, onc, 1, 1))
     assert (got - ref).abs().max().item() < 1e-12
+
+
+def test_sparse_first_conv_of_the_flow_network_equals_the_dense_conv():
+    """csrc/flownet.cu: fbbox_kernel + fconv_sparse_kernel.  The first conv of netF (7x7, pad 3; reference layer
+    Module2/intrinsic_flow_models/networks.py:601) reads key-point discs: per output pixel only the (channel, tap) pairs
+    whose input lies inside the channel's non-zero bounding box are visited.  This restates the kernel's loops (tile-level
+    box test, per-pixel window, slab index into the packed weights [ky*k+kx][Cin][Cout]) in numpy and compares with
+    F.conv2d, including an empty plane, a disc cut by the border and a plane that is dense."""
+    import numpy as np
+    g = torch.Generator().manual_seed(3)
+    H = W = 40
+    Cin, Cout, k, pad = 6, 5, 7, 3
+    x = torch.zeros(1, Cin, H, W, dtype=torch.float64)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for c, (cy, cx) in enumerate([(10.3, 12.7), (1.2, 38.9), (39.0, 0.0), (20.5, 20.5)]):
+        x[0, c] = torch.from_numpy(((xx - cx) ** 2 + (yy - cy) ** 2 <= 16).astype(np.float64))
+    x[0, 5] = torch.randn(H, W, generator=g, dtype=torch.float64)   # dense plane; plane 4 stays empty
+    w = torch.randn(Cout, Cin, k, k, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, padding=pad)[0].numpy()
+    packed = w.permute(2, 3, 1, 0).reshape(k * k, Cin, Cout).numpy()   # [slab][Cin][Cout], slab = ky*k + kx
+    xn = x[0].numpy()
+    bbox = []
+    for c in range(Cin):
+        nz = np.argwhere(xn[c] != 0)
+        bbox.append((H, -1, W, -1) if len(nz) == 0 else (nz[:, 0].min(), nz[:, 0].max(), nz[:, 1].min(), nz[:, 1].max()))
+    out = np.zeros((Cout, H, W))
+    visited = 0
+    for ty0 in range(0, H, 16):
+        for tx0 in range(0, W, 16):
+            ry0, ry1, rx0, rx1 = ty0 - pad, ty0 + 15 - pad + k - 1, tx0 - pad, tx0 + 15 - pad + k - 1
+            for c in range(Cin):
+                y0, y1, x0, x1 = bbox[c]
+                if y1 < ry0 or y0 > ry1 or x1 < rx0 or x0 > rx1:
+                    continue
+                for y in range(ty0, min(ty0 + 16, H)):
+                    for xq in range(tx0, min(tx0 + 16, W)):
+                        wy0, wx0 = y - pad, xq - pad
+                        for iy in range(max(wy0, y0), min(wy0 + k - 1, y1) + 1):
+                            for ix in range(max(wx0, x0), min(wx0 + k - 1, x1) + 1):
+                                v = xn[c, iy, ix]
+                                if v != 0:
+                                    visited += 1
+                                    out[:, y, xq] += v * packed[(iy - wy0) * k + (ix - wx0), c]
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    assert visited < 0.5 * H * W * Cin * k * k   # and most of the dense conv's terms were never touched
