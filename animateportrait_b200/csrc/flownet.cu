@@ -198,27 +198,24 @@ __global__ void __launch_bounds__(256, 2) fconv_tiled_kernel(const __grid_consta
     l_x[r] = pix - l_y[r] * p.Wv;
   }
 
+  // activation as one select: LeakyReLU slope (1 = identity, 0 = ReLU)
+  const float slope = p.act == FACT_LRELU01 ? 0.1f : p.act == FACT_LRELU02 ? 0.2f : p.act == FACT_RELU ? 0.f : 1.f;
   float4 ra[2], rb[NBV];
+  bool r_ok[2];
+  // fetch(step): issue the global loads of a step into registers and nothing else -- the operand transform waits until
+  // stash(), after the FMAs of the current step, so that the load latency sits under them
   auto fetch = [&](int step) {
     const int t = step / steps_per_tap;
-    const int c = (step - t * steps_per_tap) * FT_BK + 4 * q;
+    const int cb = (step - t * steps_per_tap) * FT_BK;
     const int dy = taps[t].dy, dx = taps[t].dx, slab = taps[t].slab;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const int iy = l_y[r] * p.stride + dy, ix = l_x[r] * p.stride + dx;
-      if (l_ok[r] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
-        v = *reinterpret_cast<const float4*>(p.in + ((size_t)(l_img[r] * p.Hin + iy) * p.Win + ix) * p.in_C + p.in_coff + c);
-        if (p.scale) {
-          const float4 sc = *reinterpret_cast<const float4*>(p.scale + (size_t)l_img[r] * p.in_C + p.in_coff + c);
-          const float4 sh = *reinterpret_cast<const float4*>(p.shift + (size_t)l_img[r] * p.in_C + p.in_coff + c);
-          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-        }
-        v.x = fact(v.x, p.act); v.y = fact(v.y, p.act); v.z = fact(v.z, p.act); v.w = fact(v.w, p.act);
-      }
-      ra[r] = v;
+      r_ok[r] = l_ok[r] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+      ra[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_ok[r])
+        ra[r] = *reinterpret_cast<const float4*>(p.in + ((size_t)(l_img[r] * p.Hin + iy) * p.Win + ix) * p.in_C + p.in_coff + cb + 4 * q);
     }
-    const int cb = (step - t * steps_per_tap) * FT_BK;
 #pragma unroll
     for (int i = 0; i < NBV; ++i) {
       const int e = tid + 256 * i;               // vector index: row kk = e / (BN/4), column (e % (BN/4)) * 4
@@ -229,14 +226,25 @@ __global__ void __launch_bounds__(256, 2) fconv_tiled_kernel(const __grid_consta
       rb[i] = w;
     }
   };
-  auto stash = [&](int buf) {
+  auto stash = [&](int buf, int step) {
+    const int c = (step % steps_per_tap) * FT_BK + 4 * q;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
+      float4 v = ra[r];
+      if (r_ok[r]) {  // zero padding applies to the activated tensor: out-of-range taps stay 0
+        if (p.scale) {
+          const float4 sc = *reinterpret_cast<const float4*>(p.scale + (size_t)l_img[r] * p.in_C + p.in_coff + c);
+          const float4 sh = *reinterpret_cast<const float4*>(p.shift + (size_t)l_img[r] * p.in_C + p.in_coff + c);
+          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        }
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      }
       const int lm = (tid >> 2) + 64 * r;
-      As[buf][4 * q + 0][lm] = ra[r].x;
-      As[buf][4 * q + 1][lm] = ra[r].y;
-      As[buf][4 * q + 2][lm] = ra[r].z;
-      As[buf][4 * q + 3][lm] = ra[r].w;
+      As[buf][4 * q + 0][lm] = v.x;
+      As[buf][4 * q + 1][lm] = v.y;
+      As[buf][4 * q + 2][lm] = v.z;
+      As[buf][4 * q + 3][lm] = v.w;
     }
 #pragma unroll
     for (int i = 0; i < NBV; ++i) {
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tiled_kernel(const __grid_consta
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   fetch(0);
-  stash(0);
+  stash(0, 0);
   __syncthreads();
   for (int step = 0; step < nsteps; ++step) {
     const int buf = step & 1;
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(256, 2) fconv_tiled_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    if (step + 1 < nsteps) stash(buf ^ 1);
+    if (step + 1 < nsteps) stash(buf ^ 1, step + 1);
     __syncthreads();
   }
 
@@ -362,7 +370,8 @@ struct FSparseP {
 };
 constexpr int FS_MAXC = 512;
 
-// grid (tiles of 16 x 16 output pixels, groups of 16 output channels, images); a thread owns one pixel and 16 channels
+// grid (tiles of 16 x 16 output pixels, groups of CG output channels, images); a thread owns one pixel and CG channels
+template <int CG>
 __global__ void __launch_bounds__(256) fconv_sparse_kernel(const __grid_constant__ FSparseP p) {
   const int n = blockIdx.z;
   if (p.area[n] > p.thresh) return;  // dense image: fconv_kernel's
@@ -372,11 +381,11 @@ __global__ void __launch_bounds__(256) fconv_sparse_kernel(const __grid_constant
   const int tiles_x = (p.W + 15) / 16;
   const int ty0 = (blockIdx.x / tiles_x) * 16, tx0 = (blockIdx.x % tiles_x) * 16;
   const int y = ty0 + (threadIdx.x >> 4), x = tx0 + (threadIdx.x & 15);
-  const int cg = blockIdx.y * 16;
+  const int cg = blockIdx.y * CG;
   if (y >= p.H || x >= p.W) return;
-  float acc[16];
+  float acc[CG];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int j = 0; j < CG; ++j) acc[j] = 0.f;
   // input rows of output row y: y - pad .. y - pad + k - 1
   const int wy0 = y - p.pad, wy1 = y - p.pad + p.k - 1, wx0 = x - p.pad, wx1 = x - p.pad + p.k - 1;
   const int ry0 = ty0 - p.pad, ry1 = ty0 + 15 - p.pad + p.k - 1, rx0 = tx0 - p.pad, rx1 = tx0 + 15 - p.pad + p.k - 1;
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(256) fconv_sparse_kernel(const __grid_constant
           const int slab = (iy - wy0) * p.k + (ix - wx0);
           const float* wp = p.w + ((size_t)slab * p.Cin + c) * p.CoutP + cg;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
+          for (int g = 0; g < CG / 4; ++g)
             if (cg + 4 * g < p.CoutP) {
               const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + 4 * g));
               acc[4 * g + 0] = fmaf(v, w4.x, acc[4 * g + 0]);
@@ -404,9 +413,25 @@ __global__ void __launch_bounds__(256) fconv_sparse_kernel(const __grid_constant
       }
   }
   float* dst = p.out + ((size_t)(n * p.H + y) * p.W + x) * p.out_C + p.out_coff;
+  if ((p.out_C & 3) == 0 && (p.out_coff & 3) == 0) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (cg + j < p.Cout) dst[cg + j] = acc[j] + (p.bias ? p.bias[cg + j] : 0.f);
+    for (int g = 0; g < CG / 4; ++g) {
+      const int c = cg + 4 * g;
+      if (c + 3 < p.Cout) {
+        float4 o = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+        if (p.bias) { o.x += p.bias[c]; o.y += p.bias[c + 1]; o.z += p.bias[c + 2]; o.w += p.bias[c + 3]; }
+        *reinterpret_cast<float4*>(dst + c) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < p.Cout) dst[c + j] = acc[4 * g + j] + (p.bias ? p.bias[c + j] : 0.f);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CG; ++j)
+      if (cg + j < p.Cout) dst[cg + j] = acc[j] + (p.bias ? p.bias[cg + j] : 0.f);
+  }
 }
 
 // InstanceNorm2d(affine=False) of a raw NHWC plane as an operand transform: scale = rstd, shift = -mean * rstd.
@@ -688,7 +713,8 @@ static int flow_conv_sparse(ap_flow* h, int B, const float* in, int Hin, const F
   sp.w = w.w; sp.bias = w.bias; sp.out = out; sp.out_C = out_C; sp.out_coff = 0;
   sp.B = B; sp.H = Hin; sp.W = Hin; sp.Cin = w.cin; sp.Cout = w.cout; sp.CoutP = w.coutp; sp.k = w.k; sp.pad = pad;
   const int tiles = (Hin + 15) / 16;
-  fconv_sparse_kernel<<<dim3(tiles * tiles, (w.cout + 15) / 16, B), 256, 0, st>>>(sp);
+  if (w.cout > 16) fconv_sparse_kernel<32><<<dim3(tiles * tiles, (w.cout + 31) / 32, B), 256, 0, st>>>(sp);
+  else fconv_sparse_kernel<16><<<dim3(tiles * tiles, 1, B), 256, 0, st>>>(sp);
   AP_CUDA(cudaGetLastError());
   launches_add(2);
   return flow_conv(h, B, in, 1, w.cin, 0, nullptr, nullptr, FACT_NONE, Hin, w, 1, 0, pad, out, out_C, 0, Hout, st, h->area,
