@@ -26,6 +26,7 @@
 
 #include "../../include/ap_flow.h"
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace ap {
 
@@ -472,6 +473,240 @@ __global__ void fbroadcast_kernel(const float* __restrict__ sc, const float* __r
   shift[(size_t)n * C + coff + c] = sh[c];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core version of the same implicit GEMM (tcgen05.mma kind::f16, fp32 accumulators in TMEM) for the layers with
+// Cin % 64 == 0 and Cout % 64 == 0 -- every conv of the U-Net proper at nf >= 32.  fp32 accuracy comes from the scheme the
+// generator's convs use: operands split as x = hi + lo (bf16 each), three products A_hi*W_hi + A_hi*W_lo + A_lo*W_hi.
+//
+// One CTA per (image, 128-pixel tile, BN-channel tile, phase).  The 4x4 stride-2 convs and the four 2x2 phases of the
+// transposed conv live on 112/56/28/14/7-pixel grids, so TMA boxes do not fit; the A operand is BUILT: eight builder
+// warps (two threads per pixel row, 32 channels each) read the raw fp32 NHWC activations of one (tap, 64-channel chunk),
+// apply the producer's normalisation and activation, split into hi/lo and write the 128-byte-swizzled K-major tile
+// tcgen05.mma reads (the same layout the stem kernel of the generator builds).  Weights are packed once, at load time,
+// as pre-swizzled [slab][chunk][plane][Cout][64] bf16 images, so a stage's W tile is two plain bulk copies.
+// Warp roles (448 threads): warp 0 = TMEM allocation + MMA issuer, warp 1 = W loader, warps 2..9 = A builders,
+// warps 10..13 = epilogue (tcgen05.ld -> 128 contiguous bytes per pixel row -> global, bias added).
+// A ring of NS stages; one `full` barrier per stage collects the 256 builder arrivals and the W bytes, one `empty`
+// barrier (tcgen05.commit) releases the stage to both producers.
+// ---------------------------------------------------------------------------------------------------------------
+struct FUmmaP {
+  FConvP c;              // geometry, operand transform, taps, output placement (c.w unused)
+  const uint8_t* wimg;   // [slab][Cin/64][2 planes][Cout rows][64 k] bf16, rows 128-byte swizzled in groups of 8
+  int tiles_per_img;     // ceil(Hv * Wv / 128)
+};
+
+constexpr int FU_THREADS = 448;
+constexpr int FU_APLANE = 128 * 128;     // [128 rows x 64 k] bf16
+constexpr int FU_ASTAGE = 2 * FU_APLANE; // hi + lo
+constexpr int FU_MAXC = 1024;            // operand channels whose scale / shift are staged in shared memory
+
+template <int BN>
+struct FUCfg {
+  static constexpr int NS = BN >= 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int WPLANE = BN * 128;
+  static constexpr int STAGE = FU_ASTAGE + 2 * WPLANE;
+  static constexpr size_t SMEM = 1024 + (size_t)NS * STAGE + 2 * FU_MAXC * 4 + 128;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_constant__ FUmmaP pp) {
+  using Cfg = FUCfg<BN>;
+  constexpr int NS = Cfg::NS;
+  const FConvP& p = pp.c;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // layout: NS stages {A hi | A lo | W hi | W lo} | scale[FU_MAXC] | shift[FU_MAXC] | barriers
+  float* s_scale = reinterpret_cast<float*>(sgen + (size_t)NS * Cfg::STAGE);
+  float* s_shift = s_scale + FU_MAXC;
+  const uint32_t bars = smem_base + NS * Cfg::STAGE + 2 * FU_MAXC * 4;
+  // full[s] +8s, empty[s] +32+8s, tfull +64, tmem pointer +72
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sgen + (size_t)NS * Cfg::STAGE + 2 * FU_MAXC * 4 + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = p.Hv * p.Wv;
+  const int img = blockIdx.x / pp.tiles_per_img;
+  const int pix0 = (blockIdx.x - img * pp.tiles_per_img) * 128;
+  const int n0 = blockIdx.y * BN;
+  const int ph = blockIdx.z;
+  const int ncb = p.Cin >> 6;
+  const int nchunks = p.ntaps * ncb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(bars + 8 * s, 257);       // full: 256 builder threads + the W loader's expect_tx arrival
+        mbar_init(bars + 32 + 8 * s, 1);    // empty: one tcgen05.commit
+      }
+      mbar_init(bars + 64, 1);              // accumulator complete
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.scale) {  // the tile lies in ONE image: its per-channel affine is staged once
+    for (int c = threadIdx.x; c < p.Cin; c += FU_THREADS) {
+      s_scale[c] = p.scale[(size_t)img * p.in_C + p.in_coff + c];
+      s_shift[c] = p.shift[(size_t)img * p.in_C + p.in_coff + c];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t accum = 0;
+      for (int s = 0; s < nchunks; ++s) {
+        const int st = s % NS;
+        mbar_wait(bars + 8 * st, (uint32_t)(s / NS) & 1u);
+        tc_fence_after();
+        const uint32_t sa = smem_base + st * Cfg::STAGE;
+        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + FU_APLANE);
+        const uint64_t w_hi = make_sw128_desc(sa + FU_ASTAGE), w_lo = make_sw128_desc(sa + FU_ASTAGE + Cfg::WPLANE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_bf16(tmem_base, a_hi + o, w_hi + o, idesc, accum);
+          accum = 1;
+          umma_bf16(tmem_base, a_hi + o, w_lo + o, idesc, 1);
+          umma_bf16(tmem_base, a_lo + o, w_hi + o, idesc, 1);
+        }
+        umma_commit(bars + 32 + 8 * st);
+      }
+      umma_commit(bars + 64);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== W loader =====================
+    if (lane == 0) {
+      const size_t plane_bytes = (size_t)p.Cout * 128;
+      for (int s = 0; s < nchunks; ++s) {
+        const int st = s % NS;
+        mbar_wait(bars + 32 + 8 * st, ((uint32_t)(s / NS) & 1u) ^ 1u);
+        const int t = s / ncb, cb = s - t * ncb;
+        const int slab = p.taps[ph][t].slab;
+        const uint8_t* src = pp.wimg + ((size_t)slab * ncb + cb) * 2 * plane_bytes + (size_t)(n0 >> 3) * 1024;
+        const uint32_t dst = smem_base + st * Cfg::STAGE + FU_ASTAGE;
+        mbar_expect_tx(bars + 8 * st, 2u * Cfg::WPLANE);
+        bulk_load(dst, src, Cfg::WPLANE, bars + 8 * st);
+        bulk_load(dst + Cfg::WPLANE, src + plane_bytes, Cfg::WPLANE, bars + 8 * st);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // ===================== A builders: thread = (pixel row, 32-channel half) =====================
+    const int bt = threadIdx.x - 64;
+    const int row = bt & 127, half = bt >> 7;
+    const int pix = pix0 + row;
+    const bool row_ok = pix < HW;
+    const int vy = row_ok ? pix / p.Wv : 0, vx = row_ok ? pix - (pix / p.Wv) * p.Wv : 0;
+    const int r8 = row & 7;
+    const int atom_off = (row >> 3) * 1024 + r8 * 128;
+    const float slope = p.act == FACT_LRELU01 ? 0.1f : p.act == FACT_LRELU02 ? 0.2f : p.act == FACT_RELU ? 0.f : 1.f;
+    const bool has_affine = p.scale != nullptr;
+    const float* in_img = p.in + (size_t)img * p.Hin * p.Win * p.in_C + p.in_coff + half * 32;
+
+    float4 ra[8], rb[8];
+    bool oka = false, okb = false;
+    auto fetch = [&](int s, float4 (&r)[8], bool& ok) {
+      const int t = s / ncb, cb = s - t * ncb;
+      const int iy = vy * p.stride + p.taps[ph][t].dy, ix = vx * p.stride + p.taps[ph][t].dx;
+      ok = row_ok && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+      if (ok) {
+        const float4* src = reinterpret_cast<const float4*>(in_img + ((size_t)iy * p.Win + ix) * p.in_C + cb * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = src[j];
+      }
+    };
+    auto build = [&](int s, const float4 (&r)[8], bool ok) {
+      const int st = s % NS;
+      const int cb = s % ncb;
+      mbar_wait(bars + 32 + 8 * st, ((uint32_t)(s / NS) & 1u) ^ 1u);
+      uint8_t* slot = sgen + (size_t)st * Cfg::STAGE;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {     // 16-byte group g of this half: channels half*32 + 8g .. +7
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {   // zero padding applies to the activated tensor: out-of-range taps stay 0
+          float v[8] = {r[2 * g].x, r[2 * g].y, r[2 * g].z, r[2 * g].w, r[2 * g + 1].x, r[2 * g + 1].y, r[2 * g + 1].z, r[2 * g + 1].w};
+          if (has_affine) {
+            const int c = cb * 64 + half * 32 + 8 * g;
+            const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c), s1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(s_shift + c), h1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
+            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+          }
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = v[2 * e] > 0.f ? v[2 * e] : v[2 * e] * slope;
+            const float b = v[2 * e + 1] > 0.f ? v[2 * e + 1] : v[2 * e + 1] * slope;
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+            hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+            lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+          }
+          hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        const int off = atom_off + (((half * 4 + g) ^ r8) << 4);
+        *reinterpret_cast<uint4*>(slot + off) = hi;
+        *reinterpret_cast<uint4*>(slot + FU_APLANE + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + 8 * st);
+    };
+    fetch(0, ra, oka);
+    for (int s = 0; s < nchunks; s += 2) {
+      if (s + 1 < nchunks) fetch(s + 1, rb, okb);   // the next chunk's loads fly while this one is converted
+      build(s, ra, oka);
+      if (s + 1 < nchunks) {
+        if (s + 2 < nchunks) fetch(s + 2, ra, oka);
+        build(s + 1, rb, okb);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 10..13): TMEM lane quarter warp & 3 =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int pix = pix0 + row;
+    const bool row_ok = pix < HW;
+    const int vy = row_ok ? pix / p.Wv : 0, vx = row_ok ? pix - (pix / p.Wv) * p.Wv : 0;
+    const int oy = vy * p.os + p.py[ph], ox = vx * p.os + p.px[ph];
+    float* dst = p.out + ((size_t)(img * p.Hout + oy) * p.Wout + ox) * p.out_C + p.out_coff + n0;
+    mbar_wait(bars + 64, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (p.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          *reinterpret_cast<float4*>(dst + c0 + 4 * j) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
 // upsample_bilinear2d(align_corners=False), scale factor 2: src = 0.5 * (dst + 0.5) - 0.5, clamped at 0
 struct FLerp { int i0, i1; float l0, l1; };
 __device__ __forceinline__ FLerp flerp_half(int dst, int in_size) {
@@ -555,6 +790,20 @@ using namespace ap;
 // =================================================================================================
 namespace {
 
+// host-side bf16 round-to-nearest-even (what __float2bfloat16_rn does on the device)
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN stays NaN
+  return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 struct FLayerW {
   float* w = nullptr;     // [slab][Cin][CoutP]
   float* bias = nullptr;  // [Cout] applied in the conv epilogue, or null
@@ -562,6 +811,8 @@ struct FLayerW {
   float* nsh = nullptr;
   int cout = 0, cin = 0, k = 0, coutp = 0;
   bool transposed = false;
+  uint8_t* wimg = nullptr;  // tensor-core path: pre-swizzled bf16 hi/lo image (fconv_umma_kernel), or null
+  int bn = 0;               // its N tile
 };
 
 struct FBuf {
@@ -590,6 +841,7 @@ struct ap_flow {
   int4* bbox = nullptr;  // [B * input_nc] non-zero bounding boxes of the operand planes of the first conv
   int* area = nullptr;   // [B] their summed areas
   int sparse = 1, tiled = 1;  // AP_FLOW_SPARSE / AP_FLOW_TILED = 0: the one generic kernel everywhere (A/B, tests)
+  int umma = 1;               // AP_FLOW_UMMA = 0: no tensor-core convs (fp32 FFMA kernels only)
   int64_t last_launches = 0;
 };
 
@@ -684,8 +936,18 @@ static int flow_conv(ap_flow* h, int B, const float* in, int in_nchw, int in_C, 
   }
   const int M = B * p.Hv * p.Wv;
   if (gate_area) { p.gate_area = gate_area; p.gate_thresh = gate_thresh; }
-  if (h->tiled && !in_nchw && !gate_area && w.cin % FT_BK == 0 && in_C % 4 == 0 && in_coff % 4 == 0 && out_C % 4 == 0 &&
+  const bool aligned4 = in_C % 4 == 0 && in_coff % 4 == 0 && out_C % 4 == 0 && out_coff % 4 == 0;
+  if (h->umma && w.wimg && !in_nchw && !gate_area && aligned4 && w.cin <= FU_MAXC) {
+    FUmmaP up;
+    up.c = p;
+    up.wimg = w.wimg;
+    up.tiles_per_img = (p.Hv * p.Wv + 127) / 128;
+    const dim3 grid((unsigned)(B * up.tiles_per_img), (unsigned)(w.cout / w.bn), (unsigned)p.nphase);
+    if (w.bn == 128) fconv_umma_kernel<128><<<grid, FU_THREADS, FUCfg<128>::SMEM, st>>>(up);
+    else fconv_umma_kernel<64><<<grid, FU_THREADS, FUCfg<64>::SMEM, st>>>(up);
+  } else if (h->tiled && !in_nchw && !gate_area && w.cin % FT_BK == 0 && in_C % 4 == 0 && in_coff % 4 == 0 && out_C % 4 == 0 &&
       out_coff % 4 == 0) {
+    (void)aligned4;
     const int mt = (M + FT_BM - 1) / FT_BM;
     if (w.cout > 64) fconv_tiled_kernel<128><<<dim3(mt, (w.cout + 127) / 128, p.nphase), 256, 0, st>>>(p);
     else if (w.cout > 16) fconv_tiled_kernel<64><<<dim3(mt, 1, p.nphase), 256, 0, st>>>(p);
@@ -752,6 +1014,21 @@ int ap_flow_create(ap_flow** handle, int input_nc, int nf, int start_scale, int 
   h->max_nf = max_nf; h->size = size; h->device = device;
   { const char* e = getenv("AP_FLOW_SPARSE"); if (e && e[0] == '0') h->sparse = 0; }
   { const char* e = getenv("AP_FLOW_TILED"); if (e && e[0] == '0') h->tiled = 0; }
+  { const char* e = getenv("AP_FLOW_UMMA"); if (e && e[0] == '0') h->umma = 0; }
+  if (h->umma) {  // function attributes are per device: set them for this handle's device
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e1 = cudaSetDevice(device);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(fconv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUCfg<64>::SMEM);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(fconv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUCfg<128>::SMEM);
+    cudaSetDevice(prev);
+    if (e1 != cudaSuccess) {
+      delete h;
+      set_error("FlowUnet: tcgen05 kernels unavailable on device %d: %s", device, cudaGetErrorString(e1));
+      cudaGetLastError();
+      return AP_ERR_UNSUPPORTED;
+    }
+  }
   int s = size, nc = nf;
   for (int sc = start_scale; sc > 1; sc /= 2) {
     s = (s + 2 - 3) / 2 + 1;
@@ -829,6 +1106,28 @@ int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const floa
           packed[((size_t)sl * cin + ci) * lw.coutp + co] = wt[s_];
         }
     AP_TRY(upload(packed, &lw.w));
+    if (h->umma && cin % 64 == 0 && (cout == 64 || cout % 128 == 0)) {
+      // tensor-core operand image: [slab][cin/64][plane hi|lo][cout rows][64 k] bf16, 8-row groups of 1024 bytes, the 16-byte
+      // groups of a row XOR-swizzled with the row index (the K-major SWIZZLE_128B layout tcgen05.mma reads)
+      const int ncb = cin / 64;
+      std::vector<uint16_t> img((size_t)k * k * cin * cout * 2);
+      for (int sl = 0; sl < k * k; ++sl)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int co = 0; co < cout; ++co) {
+            const float wv = packed[((size_t)sl * cin + ci) * lw.coutp + co];
+            const uint16_t hi = f32_to_bf16(wv);
+            const uint16_t lo = f32_to_bf16(wv - bf16_to_f32(hi));
+            const int cb = ci >> 6, kk = ci & 63;
+            const size_t row = (size_t)(co >> 3) * 1024 + (size_t)(co & 7) * 128 + (size_t)(((kk >> 3) ^ (co & 7)) << 4) + (size_t)(kk & 7) * 2;
+            const size_t base = (((size_t)sl * ncb + cb) * 2) * (size_t)cout * 128;
+            img[(base + row) / 2] = hi;
+            img[(base + (size_t)cout * 128 + row) / 2] = lo;
+          }
+      AP_CUDA(cudaMalloc((void**)&lw.wimg, img.size() * 2));
+      h->owned.push_back(lw.wimg);
+      AP_CUDA(cudaMemcpy(lw.wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+      lw.bn = cout == 64 ? 64 : 128;
+    }
     if (has_bias) AP_TRY(host_copy(key + ".bias", cout, &bias));
     if (normkey.empty()) {
       if (has_bias) AP_TRY(upload(bias, &lw.bias));

@@ -142,10 +142,11 @@ def test_clip_renderer_makes_its_own_flow_with_netF():
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("cfg", [(16, 2, 4, "batch"), (8, 1, 5, "instance"), (32, 2, 4, "instance")])
-def test_sparse_and_tiled_kernels_agree_with_the_generic_kernel(cfg, monkeypatch):
-    """The default path (box-restricted first conv + register-tiled implicit GEMM, csrc/flownet.cu) against the one
-    generic kernel it replaced (AP_FLOW_SPARSE=0 AP_FLOW_TILED=0): same sums, other association."""
+@pytest.mark.parametrize("cfg", [(16, 2, 4, "batch"), (8, 1, 5, "instance"), (32, 2, 4, "instance"), (64, 2, 3, "batch")])
+def test_fast_kernels_agree_with_the_generic_kernel(cfg, monkeypatch):
+    """The default path (box-restricted first conv, tcgen05 convs where Cin % 64 == 0, register-tiled fp32 convs
+    elsewhere; csrc/flownet.cu) against the fp32 kernels alone (AP_FLOW_UMMA=0) and against the one generic kernel it all
+    replaced (AP_FLOW_SPARSE=0 AP_FLOW_TILED=0 AP_FLOW_UMMA=0): same sums, other association / a bf16 hi-lo split."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     dev = torch.device("cuda", 0)
@@ -157,15 +158,20 @@ def test_sparse_and_tiled_kernels_agree_with_the_generic_kernel(cfg, monkeypatch
         net = FlowUnet(136, nf=nf, start_scale=ss, num_scale=ns, norm=norm).to(dev).eval()
         net.load_state_dict(sd, strict=False)
         flow, vis, _, _ = net(x)
+        one, _, _, _ = net(x[1:2])
+        assert torch.equal(one, flow[1:2])      # a frame does not depend on its batch, whatever the kernels
         return flow.cpu(), vis.cpu(), net.last_launch_count()
 
     flow, vis, n_fast = run()
+    monkeypatch.setenv("AP_FLOW_UMMA", "0")
+    flow1, vis1, n_ffma = run()
     monkeypatch.setenv("AP_FLOW_SPARSE", "0")
     monkeypatch.setenv("AP_FLOW_TILED", "0")
     flow0, vis0, n_plain = run()
-    assert n_fast == n_plain + 2   # the box pass and the sparse kernel
+    assert n_fast == n_ffma == n_plain + 2   # the box pass and the sparse kernel; the other kernels replace one for one
     scale = max(1.0, flow0.abs().max().item(), vis0.abs().max().item())
-    assert (flow - flow0).abs().max().item() <= 2e-4 * scale and (vis - vis0).abs().max().item() <= 2e-4 * scale
+    assert (flow1 - flow0).abs().max().item() <= 2e-4 * scale and (vis1 - vis0).abs().max().item() <= 2e-4 * scale
+    assert (flow - flow0).abs().max().item() <= 5e-4 * scale and (vis - vis0).abs().max().item() <= 5e-4 * scale
 
 
 @pytest.mark.gpu
