@@ -484,18 +484,22 @@ __global__ void fbroadcast_kernel(const float* __restrict__ sc, const float* __r
 // apply the producer's normalisation and activation, split into hi/lo and write the 128-byte-swizzled K-major tile
 // tcgen05.mma reads (the same layout the stem kernel of the generator builds).  Weights are packed once, at load time,
 // as pre-swizzled [slab][chunk][plane][Cout][64] bf16 images, so a stage's W tile is two plain bulk copies.
-// Warp roles (448 threads): warp 0 = TMEM allocation + MMA issuer, warp 1 = W loader, warps 2..9 = A builders,
-// warps 10..13 = epilogue (tcgen05.ld -> 128 contiguous bytes per pixel row -> global, bias added).
+// Warp roles (704 threads): warp 0 = TMEM allocation + MMA issuer, warp 1 = W loader, warps 2..17 = A builders,
+// warps 18..21 = epilogue (tcgen05.ld -> 128 contiguous bytes per pixel row -> global, bias added).
 // A ring of NS stages; one `full` barrier per stage collects the 256 builder arrivals and the W bytes, one `empty`
 // barrier (tcgen05.commit) releases the stage to both producers.
 // ---------------------------------------------------------------------------------------------------------------
 struct FUmmaP {
   FConvP c;              // geometry, operand transform, taps, output placement (c.w unused)
-  const uint8_t* wimg;   // [slab][Cin/64][2 planes][Cout rows][64 k] bf16, rows 128-byte swizzled in groups of 8
+  const uint8_t* wimg;   // [slab][Cin/kc][2 planes][wrows][64 k] bf16, rows 128-byte swizzled in groups of 8
   int tiles_per_img;     // ceil(Hv * Wv / 128)
+  int kc;                // channels per K chunk: 64, or 32 when Cin is only a multiple of 32 (half-filled rows, 2 k-steps)
+  int wrows;             // rows of a weight plane: Cout, padded to 16 for the 5-channel heads
 };
 
-constexpr int FU_THREADS = 448;
+constexpr int FU_BWARPS = 16;                           // builder warps
+constexpr int FU_THREADS = 64 + 32 * FU_BWARPS + 128;   // MMA warp, W loader, builders, 4 epilogue warps
+constexpr int FU_RPT = 128 / FU_BWARPS / 2;             // rows per builder thread and chunk
 constexpr int FU_APLANE = 128 * 128;     // [128 rows x 64 k] bf16
 constexpr int FU_ASTAGE = 2 * FU_APLANE; // hi + lo
 constexpr int FU_MAXC = 1024;            // operand channels whose scale / shift are staged in shared memory
@@ -503,6 +507,7 @@ constexpr int FU_MAXC = 1024;            // operand channels whose scale / shift
 template <int BN>
 struct FUCfg {
   static constexpr int NS = BN >= 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int TCOLS = BN < 32 ? 32 : BN;   // TMEM columns (power of two >= 32)
   static constexpr int WPLANE = BN * 128;
   static constexpr int STAGE = FU_ASTAGE + 2 * WPLANE;
   static constexpr size_t SMEM = 1024 + (size_t)NS * STAGE + 2 * FU_MAXC * 4 + 128;
@@ -529,20 +534,22 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
   const int pix0 = (blockIdx.x - img * pp.tiles_per_img) * 128;
   const int n0 = blockIdx.y * BN;
   const int ph = blockIdx.z;
-  const int ncb = p.Cin >> 6;
+  const int kc = pp.kc;
+  const int ncb = p.Cin / kc;
   const int nchunks = p.ntaps * ncb;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
-        mbar_init(bars + 8 * s, 257);       // full: 256 builder threads + the W loader's expect_tx arrival
+        mbar_init(bars + 8 * s, 32 * FU_BWARPS + 1);  // full: every builder thread + the W loader's expect_tx arrival
         mbar_init(bars + 32 + 8 * s, 1);    // empty: one tcgen05.commit
       }
       mbar_init(bars + 64, 1);              // accumulator complete
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)Cfg::TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -562,6 +569,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t accum = 0;
+      const int ksteps = kc >> 4;
       for (int s = 0; s < nchunks; ++s) {
         const int st = s % NS;
         mbar_wait(bars + 8 * st, (uint32_t)(s / NS) & 1u);
@@ -569,8 +577,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
         const uint32_t sa = smem_base + st * Cfg::STAGE;
         const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + FU_APLANE);
         const uint64_t w_hi = make_sw128_desc(sa + FU_ASTAGE), w_lo = make_sw128_desc(sa + FU_ASTAGE + Cfg::WPLANE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < ksteps; ++k) {
           const uint64_t o = (uint64_t)(k * 2);
           umma_bf16(tmem_base, a_hi + o, w_hi + o, idesc, accum);
           accum = 1;
@@ -585,7 +592,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
   } else if (warp == 1) {
     // ===================== W loader =====================
     if (lane == 0) {
-      const size_t plane_bytes = (size_t)p.Cout * 128;
+      const size_t plane_bytes = (size_t)pp.wrows * 128;
       for (int s = 0; s < nchunks; ++s) {
         const int st = s % NS;
         mbar_wait(bars + 32 + 8 * st, ((uint32_t)(s / NS) & 1u) ^ 1u);
@@ -599,65 +606,79 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
       }
     }
     __syncwarp();
-  } else if (warp < 10) {
-    // ===================== A builders: thread = (pixel row, 32-channel half) =====================
-    const int bt = threadIdx.x - 64;
-    const int row = bt & 127, half = bt >> 7;
-    const int pix = pix0 + row;
-    const bool row_ok = pix < HW;
-    const int vy = row_ok ? pix / p.Wv : 0, vx = row_ok ? pix - (pix / p.Wv) * p.Wv : 0;
-    const int r8 = row & 7;
-    const int atom_off = (row >> 3) * 1024 + r8 * 128;
+  } else if (warp < 2 + FU_BWARPS) {
+    // ===================== A builders =====================
+    // A warp instruction reads two whole pixel rows of the chunk (2 x 256 contiguous bytes): lane -> (row parity, 16-byte
+    // column), builder warp w owns rows 8w .. 8w+7, FU_RPT rows per thread.  Sixteen warps: the conversion (normalise,
+    // activation, hi/lo split: ~8 instructions per element) is what bounds this kernel, not the MMAs.
+    const int bw = warp - 2;                 // 0..FU_BWARPS-1
+    const int col = lane & 15;               // channels 4*col .. 4*col+3 of the chunk
+    const int rsub = lane >> 4;
     const float slope = p.act == FACT_LRELU01 ? 0.1f : p.act == FACT_LRELU02 ? 0.2f : p.act == FACT_RELU ? 0.f : 1.f;
     const bool has_affine = p.scale != nullptr;
-    const float* in_img = p.in + (size_t)img * p.Hin * p.Win * p.in_C + p.in_coff + half * 32;
-
-    float4 ra[8], rb[8];
-    bool oka = false, okb = false;
-    auto fetch = [&](int s, float4 (&r)[8], bool& ok) {
-      const int t = s / ncb, cb = s - t * ncb;
-      const int iy = vy * p.stride + p.taps[ph][t].dy, ix = vx * p.stride + p.taps[ph][t].dx;
-      ok = row_ok && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-      if (ok) {
-        const float4* src = reinterpret_cast<const float4*>(in_img + ((size_t)iy * p.Win + ix) * p.in_C + cb * 64);
+    const float* in_img = p.in + (size_t)img * p.Hin * p.Win * p.in_C + p.in_coff + 4 * col;
+    const bool col_ok = 4 * col < kc;        // kc = 32: only the first half of a row carries data (the MMAs read 2 k-steps)
+    int ry[FU_RPT], rx[FU_RPT];              // input coordinates of tap (0,0) for this thread's rows; ry < -64: no such pixel
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = src[j];
+    for (int i = 0; i < FU_RPT; ++i) {
+      const int pix = pix0 + bw * (2 * FU_RPT) + 2 * i + rsub;
+      const int vy = pix / p.Wv;
+      ry[i] = (pix < HW && col_ok) ? vy * p.stride : -100000;
+      rx[i] = (pix - vy * p.Wv) * p.stride;
+    }
+
+    float4 ra[FU_RPT], rb[FU_RPT];
+    uint32_t oka = 0, okb = 0;
+    auto fetch = [&](int s, float4 (&r)[FU_RPT], uint32_t& ok) {
+      const int t = s / ncb, cb = s - t * ncb;
+      const int dy = p.taps[ph][t].dy, dx = p.taps[ph][t].dx;
+      ok = 0;
+#pragma unroll
+      for (int i = 0; i < FU_RPT; ++i) {
+        const int iy = ry[i] + dy, ix = rx[i] + dx;
+        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
+          ok |= 1u << i;
+          r[i] = *reinterpret_cast<const float4*>(in_img + ((size_t)iy * p.Win + ix) * p.in_C + cb * kc);
+        }
       }
     };
-    auto build = [&](int s, const float4 (&r)[8], bool ok) {
+    auto build = [&](int s, const float4 (&r)[FU_RPT], uint32_t ok) {
       const int st = s % NS;
       const int cb = s % ncb;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_affine && col_ok) {
+        sc = *reinterpret_cast<const float4*>(s_scale + cb * kc + 4 * col);
+        sh = *reinterpret_cast<const float4*>(s_shift + cb * kc + 4 * col);
+      }
       mbar_wait(bars + 32 + 8 * st, ((uint32_t)(s / NS) & 1u) ^ 1u);
       uint8_t* slot = sgen + (size_t)st * Cfg::STAGE;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {     // 16-byte group g of this half: channels half*32 + 8g .. +7
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) {   // zero padding applies to the activated tensor: out-of-range taps stay 0
-          float v[8] = {r[2 * g].x, r[2 * g].y, r[2 * g].z, r[2 * g].w, r[2 * g + 1].x, r[2 * g + 1].y, r[2 * g + 1].z, r[2 * g + 1].w};
-          if (has_affine) {
-            const int c = cb * 64 + half * 32 + 8 * g;
-            const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c), s1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(s_shift + c), h1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
-            v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-            v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-          }
-          uint32_t hw[4], lw[4];
+      for (int i = 0; i < FU_RPT; ++i) {
+        const int row = bw * (2 * FU_RPT) + 2 * i + rsub;
+        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+        if (ok & (1u << i)) {   // zero padding applies to the activated tensor: out-of-range taps stay 0
+          float v[4] = {fmaf(r[i].x, sc.x, sh.x), fmaf(r[i].y, sc.y, sh.y), fmaf(r[i].z, sc.z, sh.z), fmaf(r[i].w, sc.w, sh.w)};
+          uint32_t hw[2], lw[2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = v[2 * e] > 0.f ? v[2 * e] : v[2 * e] * slope;
-            const float b = v[2 * e + 1] > 0.f ? v[2 * e + 1] : v[2 * e + 1] * slope;
-            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-            hw[e] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-            lw[e] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+          for (int e = 0; e < 2; ++e) {
+            // LeakyReLU with 0 <= slope <= 1 is max(v, slope * v); slope = 1: identity
+            const float a = fmaxf(v[2 * e], v[2 * e] * slope), b = fmaxf(v[2 * e + 1], v[2 * e + 1] * slope);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);   // one packed conversion per pair
+            const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
+            const float ra_ = a - __uint_as_float(hbits << 16), rb_ = b - __uint_as_float(hbits & 0xffff0000u);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(ra_, rb_);
+            hw[e] = hbits;
+            lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          hi = make_uint2(hw[0], hw[1]);
+          lo = make_uint2(lw[0], lw[1]);
         }
-        const int off = atom_off + (((half * 4 + g) ^ r8) << 4);
-        *reinterpret_cast<uint4*>(slot + off) = hi;
-        *reinterpret_cast<uint4*>(slot + FU_APLANE + off) = lo;
+        // row `row` of the K-major SWIZZLE_128B tile; 16-byte group col/2, 8-byte half col&1
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1) * 8;
+        if (col_ok) {
+          *reinterpret_cast<uint2*>(slot + off) = hi;
+          *reinterpret_cast<uint2*>(slot + FU_APLANE + off) = lo;
+        }
       }
       fence_proxy_async();
       mbar_arrive(bars + 8 * st);
@@ -672,7 +693,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
       }
     }
   } else {
-    // ===================== epilogue (warps 10..13): TMEM lane quarter warp & 3 =====================
+    // ===================== epilogue (last four warps): TMEM lane quarter warp & 3 =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int pix = pix0 + row;
@@ -689,6 +710,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
       if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          if (c0 + 4 * j >= BN || n0 + c0 + 4 * j >= p.CoutP) continue;   // narrow heads: 5 channels in an 8-channel buffer
           float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           if (p.bias) {
             const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j);
@@ -703,7 +725,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TCOLS) : "memory");
   }
 }
 
@@ -812,7 +834,7 @@ struct FLayerW {
   int cout = 0, cin = 0, k = 0, coutp = 0;
   bool transposed = false;
   uint8_t* wimg = nullptr;  // tensor-core path: pre-swizzled bf16 hi/lo image (fconv_umma_kernel), or null
-  int bn = 0;               // its N tile
+  int bn = 0, kc = 0, wrows = 0;  // its N tile, channels per K chunk, rows per weight plane
 };
 
 struct FBuf {
@@ -842,6 +864,7 @@ struct ap_flow {
   int* area = nullptr;   // [B] their summed areas
   int sparse = 1, tiled = 1;  // AP_FLOW_SPARSE / AP_FLOW_TILED = 0: the one generic kernel everywhere (A/B, tests)
   int umma = 1;               // AP_FLOW_UMMA = 0: no tensor-core convs (fp32 FFMA kernels only)
+  int bn256 = 0;              // AP_FLOW_BN256 = 1: N tile of 256 where Cout % 256 == 0 (A/B)
   int64_t last_launches = 0;
 };
 
@@ -942,9 +965,13 @@ static int flow_conv(ap_flow* h, int B, const float* in, int in_nchw, int in_C, 
     up.c = p;
     up.wimg = w.wimg;
     up.tiles_per_img = (p.Hv * p.Wv + 127) / 128;
-    const dim3 grid((unsigned)(B * up.tiles_per_img), (unsigned)(w.cout / w.bn), (unsigned)p.nphase);
-    if (w.bn == 128) fconv_umma_kernel<128><<<grid, FU_THREADS, FUCfg<128>::SMEM, st>>>(up);
-    else fconv_umma_kernel<64><<<grid, FU_THREADS, FUCfg<64>::SMEM, st>>>(up);
+    up.kc = w.kc;
+    up.wrows = w.wrows;
+    const dim3 grid((unsigned)(B * up.tiles_per_img), (unsigned)((w.cout + w.bn - 1) / w.bn), (unsigned)p.nphase);
+    if (w.bn == 256) fconv_umma_kernel<256><<<grid, FU_THREADS, FUCfg<256>::SMEM, st>>>(up);
+    else if (w.bn == 128) fconv_umma_kernel<128><<<grid, FU_THREADS, FUCfg<128>::SMEM, st>>>(up);
+    else if (w.bn == 64) fconv_umma_kernel<64><<<grid, FU_THREADS, FUCfg<64>::SMEM, st>>>(up);
+    else fconv_umma_kernel<16><<<grid, FU_THREADS, FUCfg<16>::SMEM, st>>>(up);
   } else if (h->tiled && !in_nchw && !gate_area && w.cin % FT_BK == 0 && in_C % 4 == 0 && in_coff % 4 == 0 && out_C % 4 == 0 &&
       out_coff % 4 == 0) {
     (void)aligned4;
@@ -1015,12 +1042,15 @@ int ap_flow_create(ap_flow** handle, int input_nc, int nf, int start_scale, int 
   { const char* e = getenv("AP_FLOW_SPARSE"); if (e && e[0] == '0') h->sparse = 0; }
   { const char* e = getenv("AP_FLOW_TILED"); if (e && e[0] == '0') h->tiled = 0; }
   { const char* e = getenv("AP_FLOW_UMMA"); if (e && e[0] == '0') h->umma = 0; }
+  { const char* e = getenv("AP_FLOW_BN256"); if (e) h->bn256 = e[0] == '1'; }
   if (h->umma) {  // function attributes are per device: set them for this handle's device
     int prev = 0;
     cudaGetDevice(&prev);
     cudaError_t e1 = cudaSetDevice(device);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(fconv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUCfg<64>::SMEM);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(fconv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUCfg<128>::SMEM);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(fconv_umma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUCfg<16>::SMEM);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(fconv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUCfg<256>::SMEM);
     cudaSetDevice(prev);
     if (e1 != cudaSuccess) {
       delete h;
@@ -1091,6 +1121,34 @@ int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const floa
     AP_CUDA(cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
     return AP_OK;
   };
+  // tensor-core operand image of a packed fp32 weight [slab][cin][coutp] (fconv_umma_kernel), where the layer qualifies:
+  // [slab][cin/kc][plane hi|lo][wrows][64 k] bf16, 8-row groups of 1024 bytes, the 16-byte groups of a row XOR-swizzled with
+  // the row index (the K-major SWIZZLE_128B layout tcgen05.mma reads)
+  auto make_wimg = [&](const std::vector<float>& packed, int nslab, int cin, int cout, int coutp, FLayerW* lw) -> int {
+    const int kc = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 0);
+    const int bn = (h->bn256 && cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : (cout == 64 ? 64 : (cout <= 16 ? 16 : 0)));
+    if (kc == 0 || bn == 0 || cin > FU_MAXC) return AP_OK;
+    const int wrows = bn == 16 ? 16 : cout;
+    const int ncb = cin / kc;
+    std::vector<uint16_t> img((size_t)nslab * ncb * 2 * wrows * 64, 0);
+    for (int sl = 0; sl < nslab; ++sl)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co) {
+          const float wv = packed[((size_t)sl * cin + ci) * coutp + co];
+          const uint16_t hi = f32_to_bf16(wv);
+          const uint16_t lo = f32_to_bf16(wv - bf16_to_f32(hi));
+          const int cb = ci / kc, kk = ci - cb * kc;
+          const size_t row = (size_t)(co >> 3) * 1024 + (size_t)(co & 7) * 128 + (size_t)(((kk >> 3) ^ (co & 7)) << 4) + (size_t)(kk & 7) * 2;
+          const size_t base = (((size_t)sl * ncb + cb) * 2) * (size_t)wrows * 128;
+          img[(base + row) / 2] = hi;
+          img[(base + (size_t)wrows * 128 + row) / 2] = lo;
+        }
+    AP_CUDA(cudaMalloc((void**)&lw->wimg, img.size() * 2));
+    h->owned.push_back(lw->wimg);
+    AP_CUDA(cudaMemcpy(lw->wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    lw->bn = bn; lw->kc = kc; lw->wrows = wrows;
+    return AP_OK;
+  };
   // conv `key` (Cout x Cin x k x k, or transposed Cin x Cout x k x k); `normkey` = its BatchNorm ("" = no norm after it);
   // bias_mode: 0 none, 1 epilogue bias (no norm follows), 2 bias in the checkpoint folds into the norm (or cancels)
   auto add = [&](const std::string& name, const std::string& key, int cout, int cin, int k, bool transposed,
@@ -1106,31 +1164,10 @@ int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const floa
           packed[((size_t)sl * cin + ci) * lw.coutp + co] = wt[s_];
         }
     AP_TRY(upload(packed, &lw.w));
-    if (h->umma && cin % 64 == 0 && (cout == 64 || cout % 128 == 0)) {
-      // tensor-core operand image: [slab][cin/64][plane hi|lo][cout rows][64 k] bf16, 8-row groups of 1024 bytes, the 16-byte
-      // groups of a row XOR-swizzled with the row index (the K-major SWIZZLE_128B layout tcgen05.mma reads)
-      const int ncb = cin / 64;
-      std::vector<uint16_t> img((size_t)k * k * cin * cout * 2);
-      for (int sl = 0; sl < k * k; ++sl)
-        for (int ci = 0; ci < cin; ++ci)
-          for (int co = 0; co < cout; ++co) {
-            const float wv = packed[((size_t)sl * cin + ci) * lw.coutp + co];
-            const uint16_t hi = f32_to_bf16(wv);
-            const uint16_t lo = f32_to_bf16(wv - bf16_to_f32(hi));
-            const int cb = ci >> 6, kk = ci & 63;
-            const size_t row = (size_t)(co >> 3) * 1024 + (size_t)(co & 7) * 128 + (size_t)(((kk >> 3) ^ (co & 7)) << 4) + (size_t)(kk & 7) * 2;
-            const size_t base = (((size_t)sl * ncb + cb) * 2) * (size_t)cout * 128;
-            img[(base + row) / 2] = hi;
-            img[(base + (size_t)cout * 128 + row) / 2] = lo;
-          }
-      AP_CUDA(cudaMalloc((void**)&lw.wimg, img.size() * 2));
-      h->owned.push_back(lw.wimg);
-      AP_CUDA(cudaMemcpy(lw.wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-      lw.bn = cout == 64 ? 64 : 128;
-    }
+    if (h->umma) AP_TRY(make_wimg(packed, k * k, cin, cout, lw.coutp, &lw));
     if (has_bias) AP_TRY(host_copy(key + ".bias", cout, &bias));
     if (normkey.empty()) {
-      if (has_bias) AP_TRY(upload(bias, &lw.bias));
+      if (has_bias) { bias.resize(lw.coutp, 0.f); AP_TRY(upload(bias, &lw.bias)); }  // vector reads of the epilogues
     } else if (!inorm) {
       // BatchNorm2d in eval mode: y = x * (gamma * invstd) + (beta - mean * gamma * invstd); a conv bias folds into the shift
       std::vector<float> g, b, mu, var, sc(cout), sh(cout);
@@ -1176,7 +1213,7 @@ int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const floa
     AP_TRY(host_copy("predict_vis.1.bias", 3, &bv));
     FLayerW lw;
     lw.cout = 5; lw.cin = cin; lw.k = 3; lw.coutp = 8;
-    std::vector<float> packed((size_t)9 * cin * 8, 0.f), bias(5);
+    std::vector<float> packed((size_t)9 * cin * 8, 0.f), bias(8, 0.f);
     for (int co = 0; co < 5; ++co) {
       const std::vector<float>& src = co < 2 ? wf : wv;
       const int c_ = co < 2 ? co : co - 2;
@@ -1186,6 +1223,7 @@ int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const floa
     }
     AP_TRY(upload(packed, &lw.w));
     AP_TRY(upload(bias, &lw.bias));
+    if (h->umma) AP_TRY(make_wimg(packed, 9, cin, 5, 8, &lw));
     h->w["heads"] = lw;
   }
   (void)st;
