@@ -53,6 +53,7 @@ SYMBOLS = {
     "ap_flow_load_weights": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
     "ap_flow_forward": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "ap_flow_warp_landmarks": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4),
     "ap_flow_last_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ap_last_error": (C.c_char_p, []),
     "ap_version": (C.c_char_p, []),

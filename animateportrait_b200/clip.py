@@ -42,25 +42,6 @@ class ClipRenderer:
         self.batch = int(batch)
         self.share_photo = bool(share_photo)
         self._photo = None
-        self._flow_stream = None   # netF of batch k+1 runs here while the generator renders batch k
-
-    def _flow_tensors(self, lm_batch: torch.Tensor, main: torch.cuda.Stream):
-        """flow_network_warp of one batch (geomcgt_ifw_test_model.py:62-76) on the flow stream: netF is fp32 CUDA-core
-        work, the generator tensor-core and HBM work, so the two overlap.  Returns (iw_flow, if_mask, event)."""
-        p = self._photo
-        B = lm_batch.shape[0]
-        if self._flow_stream is None:
-            self._flow_stream = torch.cuda.Stream(device=lm_batch.device)
-        side = self._flow_stream
-        side.wait_stream(main)   # the landmarks (and, first time, the source key-point maps) are made on `main`
-        with torch.cuda.stream(side):
-            kp2 = conditioning.kp_to_map_some((self.netF.size, self.netF.size), lm_batch * 7 / 8)
-            flow, ifm = self.netF.warp_tensors(torch.cat([p["kp1"].expand(B, -1, -1, -1), kp2], 1))
-            done = torch.cuda.Event()
-            done.record(side)
-        for t in (flow, ifm):
-            t.record_stream(main)
-        return flow, ifm, done
 
     @torch.no_grad()
     def set_photo(self, real_A: torch.Tensor, A_lm_68: torch.Tensor, matte: Optional[torch.Tensor] = None,
@@ -80,10 +61,7 @@ class ClipRenderer:
         if matte is not None:
             real_A, mask = conditioning.matte_photo(real_A, matte.to(dev))
         land1 = conditioning.draw2(256, 256, lm[None], 3)
-        kp1 = None
-        if self.netF is not None:  # source key-point maps of the flow network: frame-invariant
-            kp1 = conditioning.kp_to_map_some((self.netF.size, self.netF.size), lm[None] * 7 / 8)
-        self._photo = {"real_A": real_A.float().contiguous(), "lm": lm, "land1": land1, "mask": mask, "kp1": kp1,
+        self._photo = {"real_A": real_A.float().contiguous(), "lm": lm, "land1": land1, "mask": mask,
                        "static": None if fakeB_static is None else fakeB_static.to(dev, torch.float32).contiguous(),
                        "expanded": {}}
 
@@ -119,8 +97,6 @@ class ClipRenderer:
             res = out if out is not None else torch.empty((T, 256, 256, 3), dtype=torch.uint8, device=dev)
         zero_flow = ones_mask = None
         own_flow = iw_flow is None and if_mask is None and self.netF is not None
-        main = torch.cuda.current_stream(dev)
-        ahead = self._flow_tensors(lm[0:min(self.batch, T)], main) if own_flow and T > 0 else None
         for s in range(0, T, self.batch):
             e = min(s + self.batch, T)
             B = e - s
@@ -128,10 +104,10 @@ class ClipRenderer:
             land2 = conditioning.draw2(256, 256, lm[s:e], 3)
             motion = conditioning.cal_motion256(p["lm"], lm[s:e])
             if own_flow:
-                flow, ifm, done = ahead
-                # queue the next batch's flow network before this batch's generator: it runs under it
-                ahead = self._flow_tensors(lm[e:min(e + self.batch, T)], main) if e < T else None
-                main.wait_event(done)
+                # flow_network_warp of the batch, one source landmark set for all its frames (ap_flow_warp_landmarks).  (Running
+                # it on a second stream under the previous batch's generator was measured: no gain -- both are tensor-core
+                # kernels that fill every SM's shared memory, they time-slice.)
+                flow, ifm = self.netF.warp_landmarks(p["lm"], lm[s:e])
             else:
                 if iw_flow is None:
                     if zero_flow is None or zero_flow.shape[0] != B:

@@ -298,10 +298,24 @@ __global__ void __launch_bounds__(256) draw_kernel(const DrawP p) {
 // kp_to_map (binary): plane (frame, point), a thread owns 4 consecutive pixels; the distance test runs in fp64 as numpy's
 // int64 grid minus a float32 scalar does.
 // ------------------------------------------------------------------------------------------------------------------
+// Plane (t, k) = blockIdx.y lands at out + t * image_stride + k * size * size (image_stride = K * size * size: the
+// contiguous [T,K,size,size] tensor; larger: one half of a channel concatenation).  kps_image_stride = 0: the same K
+// points for every image.  pre78: the points are first scaled by 7/8 in fp32, (x * 7) / 8, as the caller of the
+// reference does (geomcgt_ifw_test_model.py:65-66: lm.numpy() * 7 / 8 on a float32 array).
+__device__ __forceinline__ float2 kp_point(const float* kps, int t, int k, int kps_image_stride, int pre78) {
+  float2 kp = reinterpret_cast<const float2*>(kps)[(size_t)t * kps_image_stride + k];
+  if (pre78) {
+    kp.x = __fdiv_rn(__fmul_rn(kp.x, 7.f), 8.f);
+    kp.y = __fdiv_rn(__fmul_rn(kp.y, 7.f), 8.f);
+  }
+  return kp;
+}
+
 __global__ void __launch_bounds__(256) kp_kernel(const float* __restrict__ kps, float* __restrict__ out, int size,
-                                                 double r2) {
+                                                 double r2, int K, size_t image_stride, int kps_image_stride, int pre78) {
   const int plane = blockIdx.y;
-  const float2 kp = reinterpret_cast<const float2*>(kps)[plane];
+  const int t = plane / K, k = plane - t * K;
+  const float2 kp = kp_point(kps, t, k, kps_image_stride, pre78);
   const bool empty = (kp.x == -1.f) || (kp.y == -1.f);
   const int quad = blockIdx.x * 256 + threadIdx.x;
   if (quad * 4 >= size * size) return;
@@ -313,7 +327,30 @@ __global__ void __launch_bounds__(256) kp_kernel(const float* __restrict__ kps, 
     const double dx = dsub((double)(x + e), (double)kp.x);
     v[e] = (!empty && dadd(dmul(dx, dx), dy2) <= r2) ? 1.f : 0.f;
   }
-  reinterpret_cast<float4*>(out)[(size_t)plane * (size * size / 4) + quad] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(out + (size_t)t * image_stride + (size_t)k * size * size)[quad] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// A box that CONTAINS the disc of every key point (floor / ceil of centre -+ radius, clipped to the map; empty for a missing
+// point or a disc off the map), written as (y0, y1, x0, x1) at bbox[t * box_image_stride + box_off + k]; the box areas of
+// an image are summed into area[t] (integer adds: order-independent).  For the zero-skipping first conv of the flow network.
+__global__ void kp_box_kernel(const float* __restrict__ kps, int T, int K, int size, float radius, int kps_image_stride,
+                              int pre78, int4* __restrict__ bbox, int box_image_stride, int box_off, int* __restrict__ area) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * K) return;
+  const int t = i / K, k = i - t * K;
+  const float2 kp = kp_point(kps, t, k, kps_image_stride, pre78);
+  int4 b = make_int4(size, -1, size, -1);
+  if (!(kp.x == -1.f || kp.y == -1.f) && kp.x == kp.x && kp.y == kp.y) {
+    const float fy0 = floorf(kp.y - radius) - 1.f, fy1 = ceilf(kp.y + radius) + 1.f;
+    const float fx0 = floorf(kp.x - radius) - 1.f, fx1 = ceilf(kp.x + radius) + 1.f;
+    const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, (float)(size - 1));
+    const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, (float)(size - 1));
+    if (y1 >= y0 && x1 >= x0) {
+      b = make_int4(y0, y1, x0, x1);
+      atomicAdd(&area[t], (y1 - y0 + 1) * (x1 - x0 + 1));
+    }
+  }
+  bbox[(size_t)t * box_image_stride + box_off + k] = b;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -415,11 +452,29 @@ extern "C" int ap_cond_kp_to_map(int device, int T, int K, int size, float radiu
   AP_REQUIRE(radius >= 0.f, AP_ERR_INVALID, "kp_to_map: negative radius");
   AP_CUDA(cudaSetDevice(device));
   dim3 grid((size * size / 4 + 255) / 256, T * K);
-  kp_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(kps, out, size, (double)radius * (double)radius);
+  kp_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(kps, out, size, (double)radius * (double)radius, K,
+                                                         (size_t)K * size * size, K, 0);
   AP_CUDA(cudaGetLastError());
   launches_add(1);
   return AP_OK;
 }
+
+namespace ap {
+// Key-point maps of one half of the flow network's input, written straight into the concatenated [T, C, size, size]
+// operand at channel `coff`, plus the boxes of their discs (flownet.cu: ap_flow_warp_landmarks).  2 launches.
+int launch_kp_half(const float* kps, int per_frame, int T, int K, int size, float radius, float* out, int C, int coff,
+                   int4* bbox, int* area, cudaStream_t st) {
+  AP_REQUIRE((long long)T * K <= 65535 && size % 4 == 0, AP_ERR_INVALID, "kp maps: at most 65535 maps per call, size %% 4 == 0");
+  dim3 grid((size * size / 4 + 255) / 256, T * K);
+  kp_kernel<<<grid, 256, 0, st>>>(kps, out + (size_t)coff * size * size, size, (double)radius * (double)radius, K,
+                                  (size_t)C * size * size, per_frame ? K : 0, 1);
+  AP_CUDA(cudaGetLastError());
+  kp_box_kernel<<<(T * K + 255) / 256, 256, 0, st>>>(kps, T, K, size, radius, per_frame ? K : 0, 1, bbox, C, coff, area);
+  AP_CUDA(cudaGetLastError());
+  launches_add(2);
+  return AP_OK;
+}
+}  // namespace ap
 
 extern "C" int ap_cond_matte_photo(int device, int B, int C, int HW, const float* real_A, const float* matte, float* out,
                                    float* mask, void* cuda_stream) {

@@ -32,6 +32,8 @@ namespace ap {
 
 void launches_add(int n);
 int64_t launches_get();
+int launch_kp_half(const float* kps, int per_frame, int T, int K, int size, float radius, float* out, int C, int coff,
+                   int4* bbox, int* area, cudaStream_t st);
 
 enum { FACT_NONE = 0, FACT_LRELU01 = 1, FACT_LRELU02 = 2, FACT_RELU = 3 };
 
@@ -860,11 +862,13 @@ struct ap_flow {
   std::vector<FBuf> cat;   // cat[l] (l >= 1): [d_{l-1} | u_l]; cat[0] = u_0
   FBuf dinner, heads;
   float *fm = nullptr, *mk = nullptr;
+  float* kpbuf = nullptr;  // [B, input_nc, size, size] key-point maps made by ap_flow_warp_landmarks (allocated on first use)
+  int kpbufB = 0;
   int4* bbox = nullptr;  // [B * input_nc] non-zero bounding boxes of the operand planes of the first conv
   int* area = nullptr;   // [B] their summed areas
   int sparse = 1, tiled = 1;  // AP_FLOW_SPARSE / AP_FLOW_TILED = 0: the one generic kernel everywhere (A/B, tests)
   int umma = 1;               // AP_FLOW_UMMA = 0: no tensor-core convs (fp32 FFMA kernels only)
-  int bn256 = 0;              // AP_FLOW_BN256 = 1: N tile of 256 where Cout % 256 == 0 (A/B)
+  int bn256 = 1;              // AP_FLOW_BN256 = 0: N tile of 128 even where Cout % 256 == 0 (A/B: 256 halves the operand builds)
   int64_t last_launches = 0;
 };
 
@@ -880,6 +884,8 @@ static void flow_free_ws(ap_flow* h) {
   h->cds.clear();
   h->cat.clear();
   h->planB = 0;
+  h->kpbuf = nullptr;
+  h->kpbufB = 0;
 }
 
 static int flow_alloc(ap_flow* h, size_t bytes, void** p) {
@@ -896,8 +902,11 @@ static int flow_buf(ap_flow* h, int B, int H, int C, FBuf* b) {
   return AP_OK;
 }
 
+// Workspace for batches of up to B images.  Every buffer is image-major, so a smaller batch simply uses the front of it:
+// the ragged last batch of a clip (733 = 11 x 64 + 29) must not cost a device synchronisation and gigabytes of
+// cudaFree / cudaMalloc twice per clip (measured: 36 ms per batch instead of 6).
 static int flow_plan(ap_flow* h, int B) {
-  if (h->planB == B) return AP_OK;
+  if (h->planB >= B) return AP_OK;
   AP_CUDA(cudaDeviceSynchronize());
   flow_free_ws(h);
   const int L = h->num_scale;
@@ -991,10 +1000,13 @@ static int flow_conv(ap_flow* h, int B, const float* in, int in_nchw, int in_C, 
 // The first conv on a sparse NCHW operand (stride 1): boxes of the non-zeros, the sparse kernel for the images that are
 // sparse and the generic kernel, gated per image, for those that are not.
 static int flow_conv_sparse(ap_flow* h, int B, const float* in, int Hin, const FLayerW& w, int pad, float* out, int out_C,
-                            int Hout, cudaStream_t st) {
-  AP_CUDA(cudaMemsetAsync(h->area, 0, (size_t)B * sizeof(int), st));
-  fbbox_kernel<<<B * w.cin, 256, 0, st>>>(in, Hin, Hin, w.cin, h->bbox, h->area);
-  AP_CUDA(cudaGetLastError());
+                            int Hout, cudaStream_t st, bool have_boxes) {
+  if (!have_boxes) {  // (ap_flow_warp_landmarks knows the boxes of its discs from the coordinates)
+    AP_CUDA(cudaMemsetAsync(h->area, 0, (size_t)B * sizeof(int), st));
+    fbbox_kernel<<<B * w.cin, 256, 0, st>>>(in, Hin, Hin, w.cin, h->bbox, h->area);
+    AP_CUDA(cudaGetLastError());
+    launches_add(1);
+  }
   FSparseP sp;
   memset(&sp, 0, sizeof(sp));
   sp.in = in; sp.bbox = h->bbox; sp.area = h->area;
@@ -1005,7 +1017,7 @@ static int flow_conv_sparse(ap_flow* h, int B, const float* in, int Hin, const F
   if (w.cout > 16) fconv_sparse_kernel<32><<<dim3(tiles * tiles, (w.cout + 31) / 32, B), 256, 0, st>>>(sp);
   else fconv_sparse_kernel<16><<<dim3(tiles * tiles, 1, B), 256, 0, st>>>(sp);
   AP_CUDA(cudaGetLastError());
-  launches_add(2);
+  launches_add(1);
   return flow_conv(h, B, in, 1, w.cin, 0, nullptr, nullptr, FACT_NONE, Hin, w, 1, 0, pad, out, out_C, 0, Hout, st, h->area,
                    sp.thresh);
 }
@@ -1232,19 +1244,15 @@ int ap_flow_load_weights(ap_flow* h, int n, const char* const* names, const floa
   return AP_OK;
 }
 
-int ap_flow_forward(ap_flow* h, int B, const float* kp_maps, float* flow_out, float* vis_out, float* iw_flow, float* if_mask,
-                    void* cuda_stream) {
-  AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
-  AP_REQUIRE(B >= 1 && kp_maps, AP_ERR_INVALID, "bad argument");
-  AP_REQUIRE((iw_flow == nullptr) == (if_mask == nullptr), AP_ERR_INVALID, "iw_flow and if_mask come together");
-  AP_CUDA(cudaSetDevice(h->device));
-  AP_TRY(flow_plan(h, B));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  const int64_t before = launches_get();
+}  // extern "C"
+
+// the network on key-point maps already on the device; have_boxes: h->bbox / h->area describe them already
+static int flow_forward_impl(ap_flow* h, int B, const float* kp_maps, bool have_boxes, float* flow_out, float* vis_out,
+                             float* iw_flow, float* if_mask, cudaStream_t st, int64_t before) {
   const int L = h->num_scale;
   // conv_downsample: conv7x7 + norm + LeakyReLU(0.1), then 3x3 stride-2 convs (networks.py:601-612)
   if (h->sparse && h->input_nc <= FS_MAXC && h->size == (h->size + 2 * 3 - 7) + 1) {
-    AP_TRY(flow_conv_sparse(h, B, kp_maps, h->size, h->w.at("cds0"), 3, h->cds[0].p, h->cds[0].C, h->size, st));
+    AP_TRY(flow_conv_sparse(h, B, kp_maps, h->size, h->w.at("cds0"), 3, h->cds[0].p, h->cds[0].C, h->size, st, have_boxes));
   } else {
     AP_TRY(flow_conv(h, B, kp_maps, 1, h->input_nc, 0, nullptr, nullptr, FACT_NONE, h->size, h->w.at("cds0"), 1, 0, 3,
                      h->cds[0].p, h->cds[0].C, 0, h->size, st));
@@ -1294,6 +1302,40 @@ int ap_flow_forward(ap_flow* h, int B, const float* kp_maps, float* flow_out, fl
   }
   h->last_launches = launches_get() - before;
   return AP_OK;
+}
+
+extern "C" {
+
+int ap_flow_forward(ap_flow* h, int B, const float* kp_maps, float* flow_out, float* vis_out, float* iw_flow, float* if_mask,
+                    void* cuda_stream) {
+  AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1 && kp_maps, AP_ERR_INVALID, "bad argument");
+  AP_REQUIRE((iw_flow == nullptr) == (if_mask == nullptr), AP_ERR_INVALID, "iw_flow and if_mask come together");
+  AP_CUDA(cudaSetDevice(h->device));
+  AP_TRY(flow_plan(h, B));
+  return flow_forward_impl(h, B, kp_maps, false, flow_out, vis_out, iw_flow, if_mask, (cudaStream_t)cuda_stream, launches_get());
+}
+
+int ap_flow_warp_landmarks(ap_flow* h, int B, const float* lm1, int lm1_per_frame, const float* lm2, float* iw_flow,
+                           float* if_mask, void* cuda_stream) {
+  AP_REQUIRE(h != nullptr && h->loaded, AP_ERR_STATE, "forward before load_weights");
+  AP_REQUIRE(B >= 1 && lm1 && lm2 && iw_flow && if_mask, AP_ERR_INVALID, "bad argument");
+  AP_REQUIRE(h->input_nc % 2 == 0, AP_ERR_UNSUPPORTED, "input_nc = %d is not two sets of key points", h->input_nc);
+  AP_CUDA(cudaSetDevice(h->device));
+  AP_TRY(flow_plan(h, B));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (h->kpbufB < B) {  // the workspace owns the buffer (flow_free_ws releases it); sized like the plan, for its largest batch
+    AP_CUDA(cudaStreamSynchronize(st));
+    AP_TRY(flow_alloc(h, (size_t)h->planB * h->input_nc * h->size * h->size * 4, (void**)&h->kpbuf));
+    h->kpbufB = h->planB;
+  }
+  const int64_t before = launches_get();
+  const int K = h->input_nc / 2;
+  const bool boxes = h->sparse && h->input_nc <= FS_MAXC;
+  AP_CUDA(cudaMemsetAsync(h->area, 0, (size_t)B * sizeof(int), st));
+  AP_TRY(launch_kp_half(lm1, lm1_per_frame, B, K, h->size, 4.f, h->kpbuf, h->input_nc, 0, h->bbox, h->area, st));
+  AP_TRY(launch_kp_half(lm2, 1, B, K, h->size, 4.f, h->kpbuf, h->input_nc, K, h->bbox, h->area, st));
+  return flow_forward_impl(h, B, h->kpbuf, boxes, nullptr, nullptr, iw_flow, if_mask, st, before);
 }
 
 int ap_flow_last_launch_count(ap_flow* h, int64_t* count) {

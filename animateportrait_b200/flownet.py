@@ -170,6 +170,32 @@ class FlowUnet(nn.Module):
         _, _, iw, ifm = self._run(input, False, True)
         return iw, ifm
 
+    @torch.no_grad()
+    def warp_landmarks(self, lm1: torch.Tensor, lm2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """flow_network_warp from landmark coordinates (`ap_flow_warp_landmarks`): lm2 [B,K,2], lm1 [B,K,2] or ONE set
+        [K,2] shared by the batch; 256-pixel coordinates, scaled by 7/8 and drawn on the device."""
+        if not (lm1.is_cuda and lm2.is_cuda):
+            raise RuntimeError("the B200 flow network runs on CUDA tensors only (no CPU fallback)")
+        if self.training and self.norm == "batch":
+            raise RuntimeError("the B200 flow network is inference-only: call .eval()")
+        K = self.input_nc // 2
+        dev = lm2.device
+        b = lm2.detach().to(dtype=torch.float32).contiguous()
+        a = lm1.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B = b.shape[0]
+        if tuple(b.shape) != (B, K, 2) or tuple(a.shape) not in ((B, K, 2), (K, 2)):
+            raise RuntimeError(f"landmarks: expected lm2 [B,{K},2] and lm1 [B,{K},2] or [{K},2], got {tuple(lm2.shape)}, {tuple(lm1.shape)}")
+        with torch.cuda.device(dev):
+            self._sync(dev)
+            iw = torch.empty((B, 2, 256, 256), device=dev)
+            ifm = torch.empty((B, 1, 256, 256), device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(_capi.lib().ap_flow_warp_landmarks(self._handle, B, C.c_void_p(a.data_ptr()), int(a.dim() == 3),
+                                                           C.c_void_p(b.data_ptr()), C.c_void_p(iw.data_ptr()),
+                                                           C.c_void_p(ifm.data_ptr()), C.c_void_p(stream)),
+                        "ap_flow_warp_landmarks")
+        return iw, ifm
+
     def last_launch_count(self) -> int:
         n = C.c_int64(0)
         _capi.check(_capi.lib().ap_flow_last_launch_count(self._handle, C.byref(n)), "ap_flow_last_launch_count")
@@ -180,7 +206,5 @@ class FlowUnet(nn.Module):
 def flow_network_warp(netF: FlowUnet, real_A, lm1: torch.Tensor, lm2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """geomcgt_ifw_test_model.py:62-76.  lm1 / lm2 [B,68,2] source / target landmarks in 256x256 pixel coordinates
     (device tensors; `real_A` is only resized and dropped by the reference and is ignored here).  The key-point maps are
-    made on the GPU at 7/8 scale (224x224) and never leave it."""
-    k1 = conditioning.kp_to_map_some((netF.size, netF.size), lm1.to(torch.float32) * 7 / 8)
-    k2 = conditioning.kp_to_map_some((netF.size, netF.size), lm2.to(torch.float32) * 7 / 8)
-    return netF.warp_tensors(torch.cat([k1, k2], 1))
+    drawn on the GPU at 7/8 scale (224x224) straight into the network's operand (`ap_flow_warp_landmarks`)."""
+    return netF.warp_landmarks(lm1, lm2)

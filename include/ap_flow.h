@@ -49,6 +49,17 @@ int ap_flow_load_weights(ap_flow* handle, int n, const char* const* names, const
 int ap_flow_forward(ap_flow* handle, int B, const float* kp_maps, float* flow_out, float* vis_out, float* iw_flow,
                     float* if_mask, void* cuda_stream);
 
+/* Replaces: flow_network_warp(netF, real_A, lm1, lm2) as a whole (geomcgt_ifw_test_model.py:62-76; call site :274) -- the
+ * form the per-frame caller uses.  lm1 / lm2: source / target landmarks [B,K,2] (x,y) float32 in the 256x256 frame of the
+ * photo, K = input_nc / 2; lm1_per_frame = 0: lm1 is ONE set [K,2] shared by the batch (a clip is rendered from one
+ * photo).  The points are scaled by 7/8 in fp32 and drawn as binary discs of radius 4 (kp_to_map_some, :12-44, :65-66)
+ * straight into the network's operand -- no key-point tensors, no concatenation, and the zero-skipping first conv takes
+ * its boxes from the coordinates -- then the network and the arg-max / mask / rescale / resize tail run as in
+ * ap_flow_forward.  `real_A` is only resized and dropped by the reference and has no counterpart here.
+ * iw_flow [B,2,256,256], if_mask [B,1,256,256].  Asynchronous on `cuda_stream`. */
+int ap_flow_warp_landmarks(ap_flow* handle, int B, const float* lm1, int lm1_per_frame, const float* lm2, float* iw_flow,
+                           float* if_mask, void* cuda_stream);
+
 /* Kernels launched by the most recent forward (the "did the CUDA path run" counter of the tests). */
 int ap_flow_last_launch_count(ap_flow* handle, int64_t* count);
 

@@ -112,6 +112,20 @@ def test_flow_network_warp_from_landmarks():
     assert same.float().mean().item() >= 0.999
     assert ((iw.cpu() - want_iw).abs() * same).max().item() <= 0.05
     assert iw.shape == (3, 2, 256, 256) and ifm.shape == (3, 1, 256, 256)
+    # the landmark-level entry point draws the same maps into the operand itself and takes the boxes of the zero-skipping
+    # conv from the coordinates (supersets of the exact ones): bit-identical to the tensor-level call, and a shared source
+    # landmark set [68,2] equals B copies of it
+    iw2, ifm2 = net.warp_tensors(x.to(dev))
+    assert torch.equal(iw, iw2) and torch.equal(ifm, ifm2)
+    iw3, ifm3 = net.warp_landmarks(torch.from_numpy(src).to(dev), lm2.to(dev))
+    assert torch.equal(iw, iw3) and torch.equal(ifm, ifm3)
+    lm_missing = lm2.clone()
+    lm_missing[1, 5] = -8.0 / 7.0        # scales to exactly -1: the reference's "missing point" marker -> an empty map
+    xm = torch.from_numpy(np.concatenate([OC.kp_to_map(lm1.numpy() * 7 / 8), OC.kp_to_map(lm_missing.numpy() * 7 / 8)], 1))
+    assert float(xm[1, 68 + 5].sum()) == 0.0
+    iw4, ifm4 = net.warp_landmarks(lm1.to(dev), lm_missing.to(dev))
+    iw5, ifm5 = net.warp_tensors(xm.to(dev))
+    assert torch.equal(iw4, iw5) and torch.equal(ifm4, ifm5)
 
 
 @pytest.mark.gpu
