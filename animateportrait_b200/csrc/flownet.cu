@@ -621,42 +621,49 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
     const float* in_img = p.in + (size_t)img * p.Hin * p.Win * p.in_C + p.in_coff + 4 * col;
     const bool col_ok = 4 * col < kc;        // kc = 32: only the first half of a row carries data (the MMAs read 2 k-steps)
     int ry[FU_RPT], rx[FU_RPT];              // input coordinates of tap (0,0) for this thread's rows; ry < -64: no such pixel
+    int goff[FU_RPT];                        // element offset of that pixel in the image; soff: byte offset of the row's 8 bytes
+    int soff[FU_RPT];                        // in the K-major SWIZZLE_128B tile (16-byte group col/2, half col&1)
 #pragma unroll
     for (int i = 0; i < FU_RPT; ++i) {
-      const int pix = pix0 + bw * (2 * FU_RPT) + 2 * i + rsub;
+      const int row = bw * (2 * FU_RPT) + 2 * i + rsub;
+      const int pix = pix0 + row;
       const int vy = pix / p.Wv;
       ry[i] = (pix < HW && col_ok) ? vy * p.stride : -100000;
       rx[i] = (pix - vy * p.Wv) * p.stride;
+      goff[i] = ry[i] >= 0 ? (ry[i] * p.Win + rx[i]) * p.in_C : 0;
+      soff[i] = (row >> 3) * 1024 + (row & 7) * 128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1) * 8;
     }
 
     float4 ra[FU_RPT], rb[FU_RPT];
     uint32_t oka = 0, okb = 0;
-    auto fetch = [&](int s, float4 (&r)[FU_RPT], uint32_t& ok) {
-      const int t = s / ncb, cb = s - t * ncb;
-      const int dy = p.taps[ph][t].dy, dx = p.taps[ph][t].dx;
+    // chunk counters advanced incrementally (no divisions in the loop): the fetch side runs one chunk ahead of the build side
+    int f_t = 0, f_cb = 0;
+    int b_st = 0, b_cb = 0;
+    uint32_t b_par = 1u;                     // parity to wait for on empty[stage]: first use of a stage passes
+    auto fetch = [&](float4 (&r)[FU_RPT], uint32_t& ok) {
+      const int dy = p.taps[ph][f_t].dy, dx = p.taps[ph][f_t].dx;
+      const int delta = (dy * p.Win + dx) * p.in_C + f_cb * kc;
       ok = 0;
 #pragma unroll
       for (int i = 0; i < FU_RPT; ++i) {
         const int iy = ry[i] + dy, ix = rx[i] + dx;
-        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
+        if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) {
           ok |= 1u << i;
-          r[i] = *reinterpret_cast<const float4*>(in_img + ((size_t)iy * p.Win + ix) * p.in_C + cb * kc);
+          r[i] = *reinterpret_cast<const float4*>(in_img + (goff[i] + delta));
         }
       }
+      if (++f_cb == ncb) { f_cb = 0; ++f_t; }
     };
-    auto build = [&](int s, const float4 (&r)[FU_RPT], uint32_t ok) {
-      const int st = s % NS;
-      const int cb = s % ncb;
+    auto build = [&](const float4 (&r)[FU_RPT], uint32_t ok) {
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (has_affine && col_ok) {
-        sc = *reinterpret_cast<const float4*>(s_scale + cb * kc + 4 * col);
-        sh = *reinterpret_cast<const float4*>(s_shift + cb * kc + 4 * col);
+        sc = *reinterpret_cast<const float4*>(s_scale + b_cb * kc + 4 * col);
+        sh = *reinterpret_cast<const float4*>(s_shift + b_cb * kc + 4 * col);
       }
-      mbar_wait(bars + 32 + 8 * st, ((uint32_t)(s / NS) & 1u) ^ 1u);
-      uint8_t* slot = sgen + (size_t)st * Cfg::STAGE;
+      mbar_wait(bars + 32 + 8 * b_st, b_par);
+      uint8_t* slot = sgen + (size_t)b_st * Cfg::STAGE;
 #pragma unroll
       for (int i = 0; i < FU_RPT; ++i) {
-        const int row = bw * (2 * FU_RPT) + 2 * i + rsub;
         uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
         if (ok & (1u << i)) {   // zero padding applies to the activated tensor: out-of-range taps stay 0
           float v[4] = {fmaf(r[i].x, sc.x, sh.x), fmaf(r[i].y, sc.y, sh.y), fmaf(r[i].z, sc.z, sh.z), fmaf(r[i].w, sc.w, sh.w)};
@@ -675,23 +682,23 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fconv_umma_kernel(const __grid_
           hi = make_uint2(hw[0], hw[1]);
           lo = make_uint2(lw[0], lw[1]);
         }
-        // row `row` of the K-major SWIZZLE_128B tile; 16-byte group col/2, 8-byte half col&1
-        const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1) * 8;
         if (col_ok) {
-          *reinterpret_cast<uint2*>(slot + off) = hi;
-          *reinterpret_cast<uint2*>(slot + FU_APLANE + off) = lo;
+          *reinterpret_cast<uint2*>(slot + soff[i]) = hi;
+          *reinterpret_cast<uint2*>(slot + FU_APLANE + soff[i]) = lo;
         }
       }
       fence_proxy_async();
-      mbar_arrive(bars + 8 * st);
+      mbar_arrive(bars + 8 * b_st);
+      if (++b_cb == ncb) b_cb = 0;
+      if (++b_st == NS) { b_st = 0; b_par ^= 1u; }
     };
-    fetch(0, ra, oka);
+    fetch(ra, oka);
     for (int s = 0; s < nchunks; s += 2) {
-      if (s + 1 < nchunks) fetch(s + 1, rb, okb);   // the next chunk's loads fly while this one is converted
-      build(s, ra, oka);
+      if (s + 1 < nchunks) fetch(rb, okb);   // the next chunk's loads fly while this one is converted
+      build(ra, oka);
       if (s + 1 < nchunks) {
-        if (s + 2 < nchunks) fetch(s + 2, ra, oka);
-        build(s + 1, rb, okb);
+        if (s + 2 < nchunks) fetch(ra, oka);
+        build(rb, okb);
       }
     }
   } else {

@@ -43,9 +43,4 @@ def only_flow():
         e = min(s + B, T)
         flow_network_warp(netF, None, lm1[:e - s], seq_d[s:e])
 out["netF_only_12_batches"] = timed(only_flow)
-if os.environ.get("AP_CLIP_SERIAL_FLOW") is None:
-    os.environ["AP_CLIP_SERIAL_FLOW"] = "1"
-    r2 = ClipRenderer(net, batch=B, netF=netF)
-    r2.set_photo(photo.to(dev), src.to(dev), matte.to(dev), static.to(dev))
-    out["clip_with_netF_serial"] = timed(lambda: r2.render(seq_d))
 print(json.dumps(out))

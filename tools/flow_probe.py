@@ -70,7 +70,7 @@ def main():
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / a.reps
     gf = dense_gflop(nf, ss, ns)
-    print(json.dumps({"what": "flow_network_warp (key-point maps + netF + arg-max/mask/resize)", "cfg": a.cfg, "batch": a.batch,
+    print(json.dumps({"what": "flow_network_warp from landmarks (ap_flow_warp_landmarks: key-point discs + netF + arg-max/mask/resize)", "cfg": a.cfg, "batch": a.batch,
                       "ms_per_batch": ms, "ms_per_frame": ms / a.batch, "frames_per_s": 1e3 * a.batch / ms,
                       "launches": net.last_launch_count(), "dense_gflop_per_frame": gf,
                       "fp32_tflops_on_the_dense_count": sum(gf.values()) * a.batch / ms,
