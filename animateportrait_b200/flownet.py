@@ -4,8 +4,9 @@
 (Module2/intrinsic_flow_models/networks.py:577-627 with `FlowUnetSkipConnectionBlock`, :510-575), so the checkpoint
 `checkpoints/FlowReg_id_flow_faces/<epoch>_net_F.pth` loads with `load_state_dict` the day it is available; the children
 only HOLD parameters, `forward` hands the key-point maps to the C ABI.  `flow_network_warp` is the caller's per-frame use
-(Module2/models/geomcgt_ifw_test_model.py:62-76) with the key-point maps made on the GPU (conditioning.kp_to_map_some)
-and the arg-max / mask / rescale / resize tail fused behind the network.  No CPU or PyTorch fallback.
+(Module2/models/geomcgt_ifw_test_model.py:62-76) as ONE library call from the landmarks (`ap_flow_warp_landmarks`): the
+key-point discs are drawn on the GPU straight into the network's operand and the arg-max / mask / rescale / resize tail is
+fused behind the network.  No CPU or PyTorch fallback.
 """
 from __future__ import annotations
 

@@ -4,7 +4,6 @@ CPU: the landmark-sharding plumbing over gloo (world_size 2 and 3) with a stand-
 recipe against the oracle's copy.  GPU (-m gpu): ClipRenderer against the oracle's frame-by-frame restatement of the
 reference's loop (dataset item -> GeomCGTIFWTestModel.forward -> tensor2im)."""
 import os
-import socket
 
 import numpy as np
 import pytest
@@ -46,12 +45,9 @@ class _StandInRenderer:
         return img.to(torch.uint8)[:, None, None, None].expand(-1, 256, 256, 3).contiguous()
 
 
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+def _rendezvous(tmp_path):
+    """file:// rendezvous in the test's own directory: no port to pick, so no race for one between back-to-back tests"""
+    return "file://" + str(tmp_path / "rendezvous")
 
 
 def _clip(T, with_flow):
@@ -62,10 +58,9 @@ def _clip(T, with_flow):
     return lm, torch.randn(T, 2, 256, 256, generator=g), torch.rand(T, 1, 256, 256, generator=g)
 
 
-def _worker(rank, world, port, T, with_flow, out_path):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, rendezvous, T, with_flow, out_path):
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    dist.init_process_group("gloo", init_method=rendezvous, rank=rank, world_size=world)
     try:
         lm, flow, ifm = _clip(T, with_flow) if rank == 0 else (None, None, None)
         frames = render_clip_sharded(_StandInRenderer(), lm, T, torch.device("cpu"), flow, ifm)
@@ -80,7 +75,7 @@ def _worker(rank, world, port, T, with_flow, out_path):
 @pytest.mark.parametrize("world,T,with_flow", [(2, 5, False), (2, 3, True), (3, 2, False)])
 def test_sharded_clip_equals_single_process(world, T, with_flow, tmp_path):
     out = str(tmp_path / "frames.pt")
-    mp.spawn(_worker, args=(world, _free_port(), T, with_flow, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _rendezvous(tmp_path), T, with_flow, out), nprocs=world, join=True)
     got = torch.load(out)
     want = _StandInRenderer().render(*_clip(T, with_flow))
     assert got.dtype == torch.uint8 and got.shape == (T, 256, 256, 3) and torch.equal(got, want)

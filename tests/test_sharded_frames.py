@@ -4,7 +4,6 @@ The generator itself needs a B200; here `netG` is a cheap stand-in with the same
 scatter -> per-rank render -> gather path (the only multi-GPU logic of the hot path) is checked
 for ragged chunk sizes, empty shards and frame order."""
 import os
-import socket
 
 import pytest
 import torch
@@ -26,18 +25,14 @@ def _make_clip(T, seed=0):
     return [torch.randn((T,) + FRAME_SHAPES[n], generator=g) for n in INPUT_NAMES]
 
 
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+def _rendezvous(tmp_path):
+    """file:// rendezvous in the test's own directory: no port to pick, so no race for one between back-to-back tests"""
+    return "file://" + str(tmp_path / "rendezvous")
 
 
-def _worker(rank, world, port, T, batch, out_path):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, rendezvous, T, batch, out_path):
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    dist.init_process_group("gloo", init_method=rendezvous, rank=rank, world_size=world)
     try:
         clip = _make_clip(T) if rank == 0 else None
         frames = render_frames_sharded(_stand_in_netg, clip, T, 1, torch.device("cpu"), batch=batch)
@@ -52,7 +47,7 @@ def _worker(rank, world, port, T, batch, out_path):
 @pytest.mark.parametrize("world,T,batch", [(2, 5, 2), (2, 1, 4), (3, 7, 16)])
 def test_sharded_render_equals_single_process(world, T, batch, tmp_path):
     out = str(tmp_path / "frames.pt")
-    mp.spawn(_worker, args=(world, _free_port(), T, batch, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _rendezvous(tmp_path), T, batch, out), nprocs=world, join=True)
     got = torch.load(out)
     want = render_frames(_stand_in_netg, _make_clip(T), batch=3)
     assert got.shape == (T, 1, 256, 256)
