@@ -477,18 +477,20 @@ __global__ void fbroadcast_kernel(const float* __restrict__ sc, const float* __r
 
 // ---------------------------------------------------------------------------------------------------------------
 // Tensor-core version of the same implicit GEMM (tcgen05.mma kind::f16, fp32 accumulators in TMEM) for the layers with
-// Cin % 64 == 0 and Cout % 64 == 0 -- every conv of the U-Net proper at nf >= 32.  fp32 accuracy comes from the scheme the
-// generator's convs use: operands split as x = hi + lo (bf16 each), three products A_hi*W_hi + A_hi*W_lo + A_lo*W_hi.
+// Cin % 32 == 0 and Cout in {<= 16, 64, multiples of 128} -- every conv of the U-Net proper at nf >= 32, and the heads.
+// fp32 accuracy comes from the scheme the generator's convs use: operands split as x = hi + lo (bf16 each), three products
+// A_hi*W_hi + A_hi*W_lo + A_lo*W_hi.
 //
 // One CTA per (image, 128-pixel tile, BN-channel tile, phase).  The 4x4 stride-2 convs and the four 2x2 phases of the
-// transposed conv live on 112/56/28/14/7-pixel grids, so TMA boxes do not fit; the A operand is BUILT: eight builder
-// warps (two threads per pixel row, 32 channels each) read the raw fp32 NHWC activations of one (tap, 64-channel chunk),
-// apply the producer's normalisation and activation, split into hi/lo and write the 128-byte-swizzled K-major tile
-// tcgen05.mma reads (the same layout the stem kernel of the generator builds).  Weights are packed once, at load time,
-// as pre-swizzled [slab][chunk][plane][Cout][64] bf16 images, so a stage's W tile is two plain bulk copies.
+// transposed conv live on 112/56/28/14/7-pixel grids, so TMA boxes do not fit; the A operand is BUILT: sixteen builder
+// warps (a warp instruction reads two whole pixel rows of a chunk, 2 x 256 contiguous bytes) read the raw fp32 NHWC
+// activations of one (tap, 64-channel chunk), apply the producer's normalisation and activation, split into hi/lo and
+// write the 128-byte-swizzled K-major tile tcgen05.mma reads (the same layout the stem kernel of the generator builds).
+// Weights are packed once, at load time, as pre-swizzled [slab][chunk][plane][Cout][64] bf16 images, so a stage's W tile
+// is two plain bulk copies.
 // Warp roles (704 threads): warp 0 = TMEM allocation + MMA issuer, warp 1 = W loader, warps 2..17 = A builders,
 // warps 18..21 = epilogue (tcgen05.ld -> 128 contiguous bytes per pixel row -> global, bias added).
-// A ring of NS stages; one `full` barrier per stage collects the 256 builder arrivals and the W bytes, one `empty`
+// A ring of NS stages; one `full` barrier per stage collects the 512 builder arrivals and the W bytes, one `empty`
 // barrier (tcgen05.commit) releases the stage to both producers.
 // ---------------------------------------------------------------------------------------------------------------
 struct FUmmaP {
