@@ -49,6 +49,10 @@ def test_refuses_cpu_tensors_training_mode_and_inconsistent_pyramids():
     net = FlowUnet(136, nf=8, start_scale=2, num_scale=2)
     with pytest.raises(RuntimeError, match="CUDA"):
         net(torch.zeros(1, 136, 224, 224))
+    with pytest.raises(RuntimeError, match="CUDA"):       # the landmark-level entry point has no CPU path either
+        net.warp_landmarks(torch.zeros(68, 2), torch.zeros(1, 68, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        flow_network_warp(net, None, torch.zeros(1, 68, 2), torch.zeros(1, 68, 2))
     assert not FO.consistent(224, 2, 5) and FO.consistent(224, 2, 4) and FO.consistent(224, 1, 5)
 
 
