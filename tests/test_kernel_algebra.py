@@ -6,6 +6,9 @@ kernels' math and guard the index conventions used by the weight packers in anim
    Reference layer: Module2/models/networks.py:1271-1274.
 2. ReflectionPad2d(3) + Conv2d(64 -> onc, 7x7) == a per-pixel [64 x 49] channel contraction followed by a 49-term
    shifted sum (csrc/conv_out.cu).  Reference layer: Module2/models/networks.py:1277-1278.
+3. netF (csrc/flownet.cu): the zero-skipping first conv == the dense conv; the shared-memory offsets of the tensor-core
+   conv's builder warps and the host weight packer are the K-major SWIZZLE_128B layout, and the three-product bf16 split
+   is fp32-accurate; the key-point boxes derived from coordinates contain their discs (csrc/conditioning.cu).
 """
 import torch
 import torch.nn.functional as F
@@ -108,3 +111,92 @@ def test_sparse_first_conv_of_the_flow_network_equals_the_dense_conv():
                                     out[:, y, xq] += v * packed[(iy - wy0) * k + (ix - wx0), c]
     assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
     assert visited < 0.5 * H * W * Cin * k * k   # and most of the dense conv's terms were never touched
+
+
+def _bf16_rn(x):
+    """float32 -> bfloat16 (round to nearest even) -> float32, as __float2bfloat16_rn / the host packer of flownet.cu"""
+    import numpy as np
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def test_flow_tensor_core_operand_layout_and_three_product_precision():
+    """csrc/flownet.cu: fconv_umma_kernel.  (1) The builder warps' shared-memory offsets and the host packer's weight image
+    are both the K-major SWIZZLE_128B layout tcgen05.mma reads: element (row r, k) of a [rows x 64] bf16 tile lives at
+    (r>>3)*1024 + (r&7)*128 + (((k>>3) ^ (r&7)) << 4) + (k&7)*2.  (2) x = hi + lo with bf16 halves and the three products
+    A_hi*W_hi + A_hi*W_lo + A_lo*W_hi reproduce an fp32 dot product far inside the 1e-3 gate (the dropped term is 2^-16)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+
+    def canonical(r, k):
+        return (r >> 3) * 1024 + (r & 7) * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2
+
+    # (1a) builder: thread (row, col) writes the 8 bytes of channels 4*col .. 4*col+3 at soff
+    tile = np.full(128 * 128, -1, dtype=np.int64)     # byte -> (row * 64 + k) that owns it
+    for row in range(128):
+        for col in range(16):
+            soff = (row >> 3) * 1024 + (row & 7) * 128 + (((col >> 1) ^ (row & 7)) << 4) + (col & 1) * 8
+            for e in range(4):
+                k = 4 * col + e
+                assert tile[soff + 2 * e] == -1
+                tile[soff + 2 * e] = tile[soff + 2 * e + 1] = row * 64 + k
+    for r in range(128):
+        for k in range(64):
+            assert tile[canonical(r, k)] == r * 64 + k
+    # (1b) host packer: [slab][cin/kc][plane][wrows][64] with the same row swizzle; an N tile of BN rows from n0 (multiple
+    # of 8) is one contiguous block of BN * 128 bytes starting (n0 >> 3) * 1024 into the plane
+    cin, cout, kc = 128, 256, 64
+    ncb = cin // kc
+    owner = {}
+    for ci in range(cin):
+        for co in range(cout):
+            cb, kk = divmod(ci, kc)
+            row = (co >> 3) * 1024 + (co & 7) * 128 + (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2
+            base = ((0 * ncb + cb) * 2) * cout * 128
+            owner[base + row] = (ci, co)
+    n0, bn, cb = 128, 128, 1
+    block0 = ((0 * ncb + cb) * 2) * cout * 128 + (n0 >> 3) * 1024
+    for r in range(bn):
+        for k in range(64):
+            assert owner[block0 + canonical(r, k)] == (cb * kc + k, n0 + r)
+    # (2) precision of the split
+    K = 2048
+    a = rng.standard_normal(K).astype(np.float32) * np.float32(3.0)
+    w = rng.standard_normal(K).astype(np.float32) * np.float32(0.05)
+    a_hi, w_hi = _bf16_rn(a), _bf16_rn(w)
+    a_lo, w_lo = _bf16_rn(a - a_hi), _bf16_rn(w - w_hi)
+    assert np.abs((a_hi.astype(np.float64) + a_lo) - a).max() <= 2.0 ** -16 * np.abs(a).max()
+    exact = float(np.dot(a.astype(np.float64), w.astype(np.float64)))
+    three = float(np.dot(a_hi.astype(np.float64), w_hi) + np.dot(a_hi.astype(np.float64), w_lo) + np.dot(a_lo.astype(np.float64), w_hi))
+    one = float(np.dot(a_hi.astype(np.float64), w_hi))
+    scale = float(np.sqrt(np.sum((a.astype(np.float64) * w) ** 2)))
+    assert abs(three - exact) <= 1e-4 * scale and abs(one - exact) >= 10 * abs(three - exact)
+
+
+def test_key_point_boxes_from_coordinates_contain_their_discs():
+    """csrc/conditioning.cu: kp_box_kernel (used by ap_flow_warp_landmarks).  The box floor(c - r) - 1 .. ceil(c + r) + 1,
+    clipped to the map, contains every pixel of the disc (x - cx)^2 + (y - cy)^2 <= r^2 the fp64 test of kp_kernel can set
+    (Module2/models/geomcgt_ifw_test_model.py:12-37), also for centres outside the map and for the missing-point marker."""
+    import numpy as np
+    rng = np.random.default_rng(1)
+    size, r = 224, 4.0
+    yy, xx = np.mgrid[0:size, 0:size]
+    pts = np.concatenate([rng.uniform(-8, size + 8, (200, 2)), [[0.0, 0.0], [223.0, 223.0], [-4.0, 100.0], [227.0, 3.5],
+                                                                 [-1.0, 50.0], [100.25, -1.0], [-4.5, -4.5]]]).astype(np.float32)
+    for cx, cy in pts:
+        disc = ((xx - np.float64(cx)) ** 2 + (yy - np.float64(cy)) ** 2 <= r * r)
+        if cx == -1 or cy == -1:
+            disc[:] = False                                   # the reference's missing point: an empty map
+            box = None
+        else:
+            y0, y1 = int(max(np.floor(np.float32(cy - r)) - 1, 0)), int(min(np.ceil(np.float32(cy + r)) + 1, size - 1))
+            x0, x1 = int(max(np.floor(np.float32(cx - r)) - 1, 0)), int(min(np.ceil(np.float32(cx + r)) + 1, size - 1))
+            box = (y0, y1, x0, x1) if (y1 >= y0 and x1 >= x0) else None
+        if box is None:
+            assert not disc.any(), (cx, cy)
+        else:
+            inside = np.zeros_like(disc)
+            inside[box[0]:box[1] + 1, box[2]:box[3] + 1] = True
+            assert not (disc & ~inside).any(), (cx, cy, box)
+            assert (box[1] - box[0] + 1) * (box[3] - box[2] + 1) <= 13 * 13
